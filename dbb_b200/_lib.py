@@ -1,0 +1,102 @@
+"""ctypes binding of libdbbcuda.so (include/dbb_cuda.h).  There is NO CPU fallback: if the library is
+missing or CUDA is unavailable, every compute call raises."""
+import ctypes
+import os
+
+import numpy as np
+
+NUM_KMERS = 136
+SIG_STRIDE = 140
+BLOCK_BASES = 64
+MAX_K = 32
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libdbbcuda.so')
+
+c_i64 = ctypes.c_int64
+c_i32 = ctypes.c_int32
+c_vp = ctypes.c_void_p
+
+
+class DbbError(RuntimeError):
+    pass
+
+
+class PairsInput(ctypes.Structure):
+    _fields_ = [('n', c_i64), ('sig', c_vp), ('length', c_vp), ('td_bound', c_vp),
+                ('gc', c_vp), ('gc_mbin', c_vp), ('gc_lbin', c_vp), ('gc_lo', c_vp), ('gc_hi', c_vp),
+                ('gc_nm', c_i32), ('gc_nl', c_i32),
+                ('cov', c_vp), ('cov_lbin', c_vp), ('cov_lo', c_vp), ('cov_hi', c_vp), ('cov_nl', c_i32)]
+
+
+class PairsOutput(ctypes.Structure):
+    _fields_ = [('k', c_i32), ('topk_filter', c_i32), ('knn_idx', c_vp), ('knn_dist', c_vp),
+                ('count', c_vp), ('neighbour_bp', c_vp),
+                ('td_mask', c_vp), ('gc_mask', c_vp), ('cov_mask', c_vp), ('mask_words', c_i64)]
+
+
+# name -> (restype, argtypes); this table is also what tests/test_abi.py checks against the header
+SIGNATURES = {
+    'dbb_last_error': (ctypes.c_char_p, []),
+    'dbb_version': (ctypes.c_int, []),
+    'dbb_device_info': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'dbb_kmer_lut': (ctypes.c_int, [c_vp]),
+    'dbb_kmer_names': (ctypes.c_int, [c_vp]),
+    'dbb_packed_blocks': (c_i64, [c_i64]),
+    'dbb_block_offsets': (ctypes.c_int, [c_vp, c_i64, c_vp]),
+    'dbb_pack_ascii_dev': (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp]),
+    'dbb_count_plan_create': (ctypes.c_int, [c_vp, c_i64, ctypes.POINTER(c_vp)]),
+    'dbb_count_plan_destroy': (ctypes.c_int, [c_vp]),
+    'dbb_count_plan_launches': (ctypes.c_int, [c_vp]),
+    'dbb_tetra_count_dev': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    'dbb_tetra_signatures_host': (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
+    'dbb_pairs_dev': (ctypes.c_int, [ctypes.POINTER(PairsInput), c_i64, c_i64, ctypes.POINTER(PairsOutput), c_vp]),
+    'dbb_pairs_scratch_bytes': (c_i64, [c_i64, c_i64, c_i32]),
+    'dbb_pairs_host': (ctypes.c_int, [ctypes.POINTER(PairsInput), c_i64, c_i64, ctypes.POINTER(PairsOutput)]),
+    'dbb_pad_signatures_dev': (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp]),
+    'dbb_synth_ascii_dev': (ctypes.c_int, [ctypes.c_uint64, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                           c_vp, c_vp, c_vp]),
+}
+
+_LIB = None
+
+
+def lib():
+    """Load the shared library once per process (lazily: reference callers fork after constructing
+    GenomicSignatures, preprocess.py:395-413, so nothing CUDA may happen at import/__init__ time)."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise DbbError('%s is not built (run `python -m dbb_b200.build`); dbb_b200 has no CPU fallback' % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = L
+    return _LIB
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib().dbb_last_error()
+        raise DbbError('libdbbcuda error %d: %s' % (rc, msg.decode('utf-8', 'replace') if msg else '?'))
+
+
+def ptr(a):
+    """void* of a numpy array (C-contiguous) or None."""
+    if a is None:
+        return None
+    assert a.flags['C_CONTIGUOUS']
+    return a.ctypes.data_as(c_vp)
+
+
+def kmer_table():
+    """(names[136], lut256) straight from the library (no GPU needed)."""
+    L = lib()
+    names = ctypes.create_string_buffer(NUM_KMERS * 5)
+    check(L.dbb_kmer_names(names))
+    lut = np.zeros(256, dtype=np.uint8)
+    check(L.dbb_kmer_lut(ptr(lut)))
+    raw = names.raw
+    return [raw[5 * i:5 * i + 4].decode('ascii') for i in range(NUM_KMERS)], lut

@@ -1,0 +1,442 @@
+// Stage 2 (K2): all-pairs tetranucleotide (L1) distance with fused neighbour predicates, per-row
+// neighbourhood counts, optional bit masks and a fused per-row top-k.  The N x N matrix is never
+// written.
+//
+// Reference semantics (tdNeighbours.py:41-51, gcNeighbours.py:43-52, coverageNeighbours.py:41-50,
+// distributions.py:75-127): for every ordered pair (i, j), i == j included,
+//   td(i,j)  = L1(sig_i, sig_j) <  tdBound[shorter of i, j]            (strict; ties in length -> i)
+//   gc(i,j)  = lo <= GC_unbinned - GC_core <= hi, core = longer (ties -> j), bounds by (core mean-GC
+//              bin, unbinned length bin)
+//   cov(i,j) = lo <= (cov_unb - cov_core) * 100 / cov_core <= hi (cov_core <= 0 -> 0.1)
+// GC / coverage arithmetic is FP64 exactly as in the reference; the distance is FP32 (tolerance
+// 2e-6 absolute, tests/).
+//
+// Kernel shape (B200): one persistent CTA per SM, 8 warps (thread 0 also issues the TMA loads).
+//   * CTA tile 128 rows x 128 columns; warp w owns rows 16w..16w+15 against all 128 columns, lane
+//     (ty = lane/16, tx = lane%16) owns rows 16w+2i+ty and columns tx+16j (i, j < 8): an 8x8 register
+//     tile, accumulated as float2 so the inner loop is two packed FADD2 per two dimensions
+//     (d = a - b ; acc += |d|) -- one FP32 issue slot per pair-dimension instead of two.
+//   * the signature matrix is [n][140] float32 (136 + 4 zero pad = 5 K-chunks of 28 floats); TMA
+//     (cp.async.bulk.tensor.2d) stages [128 rows][28 floats] boxes: the A row tile is resident for a
+//     whole row sweep (5 boxes), B boxes stream through a 4-stage mbarrier ring.  Row pitch 112 B =
+//     7 x 16 B makes every LDS.128 of the tile walk distinct bank groups.
+//   * epilogue per column tile: predicates + counts from registers, 16-bit mask pieces by warp ballot,
+//     top-k candidates (d <= current k-th best of the row, kept in a register) are rare after the first
+//     tiles and are inserted warp-cooperatively into a sorted per-row list in shared memory.
+//     Ordering is the total order (distance, j), so results do not depend on tile schedule or on how
+//     rows are sharded over GPUs.
+#include "common.cuh"
+#include <cuda.h>
+#include <algorithm>
+#include <cfloat>
+#include <climits>
+
+namespace {
+
+constexpr int TILE = 128;
+constexpr int KCH = 28;                      // floats per K chunk
+constexpr int NKC = DBB_SIG_STRIDE / KCH;    // 5
+constexpr int NSTAGE = 4;
+constexpr int CHUNK_BYTES = TILE * KCH * 4;  // 14336
+constexpr int COMPUTE_WARPS = 8;
+constexpr int THREADS = COMPUTE_WARPS * 32;       // 8 warps: register allocation is per 4 warps
+constexpr int PREFETCH = NSTAGE - 2;             // B chunks in flight ahead of the consumer
+constexpr int LIST_K = DBB_MAX_K;            // list slots per row
+
+struct RowScalars {       // staged in shared memory per row tile
+  int32_t len;
+  float tdb;
+  int32_t gcm, gcl, covl;
+  int32_t pad;
+  double gc, cov;
+};
+
+struct Params {
+  int64_t n, row0, row1;
+  const int32_t* length;
+  const float* td_bound;
+  const double* gc; const int32_t* gc_mbin; const int32_t* gc_lbin; const double* gc_lo; const double* gc_hi; int32_t gc_nl;
+  const double* cov; const int32_t* cov_lbin; const double* cov_lo; const double* cov_hi;
+  int32_t k, topk_filter;
+  int32_t* knn_idx; float* knn_dist; int32_t* count; int64_t* neighbour_bp;
+  uint32_t* td_mask; uint32_t* gc_mask; uint32_t* cov_mask; int64_t mask_words;
+};
+
+struct SmemLayout {
+  alignas(128) float a[NKC][TILE][KCH];
+  alignas(128) float b[NSTAGE][TILE][KCH];
+  float list_d[TILE][LIST_K];
+  int32_t list_j[TILE][LIST_K];
+  RowScalars rows[TILE];
+  alignas(8) uint64_t full[NSTAGE];
+  uint64_t empty[NSTAGE];
+  uint64_t a_full;
+  uint64_t a_empty;
+};
+
+// ---- mbarrier / TMA primitives ------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t}"
+      :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int32_t x, int32_t y, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      :: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y) : "memory");
+}
+
+__device__ __forceinline__ float2 absdiff_acc(float2 acc, float2 a, float2 b) {
+  float2 d = __fadd2_rn(a, make_float2(-b.x, -b.y));
+  return __fadd2_rn(acc, make_float2(fabsf(d.x), fabsf(d.y)));
+}
+
+// warp-cooperative insertion of (d, c) into the sorted list of `row`; returns the new k-th best
+__device__ __forceinline__ float list_insert(SmemLayout& sm, int row, float d, int32_t c, int k, int lane) {
+  float ed = sm.list_d[row][lane];
+  int32_t ej = sm.list_j[row][lane];
+  const bool before = (ed < d) || (ed == d && ej < c);
+  const int pos = __popc(__ballot_sync(0xffffffffu, before));
+  float pd = __shfl_up_sync(0xffffffffu, ed, 1);
+  int32_t pj = __shfl_up_sync(0xffffffffu, ej, 1);
+  if (pos < k) {
+    if (lane == pos) { ed = d; ej = c; }
+    else if (lane > pos) { ed = pd; ej = pj; }
+    sm.list_d[row][lane] = ed;
+    sm.list_j[row][lane] = ej;
+  }
+  __syncwarp();
+  return __shfl_sync(0xffffffffu, ed, k - 1);
+}
+
+// rare path: all lanes whose bit is set in m hold a candidate (distance d) for row row2 + lane/16,
+// column colj + lane%16; returns the caller's updated k-th-best threshold
+__device__ __noinline__ float insert_candidates(SmemLayout& sm, uint32_t m, float d, float thr, int32_t colj,
+                                                int row2, int k, int lane) {
+  while (m) {
+    const int src = __ffs(m) - 1;
+    m &= m - 1;
+    const float cd = __shfl_sync(0xffffffffu, d, src);
+    const float nt = list_insert(sm, row2 + (src >> 4), cd, colj + (src & 15), k, lane);
+    if ((lane >> 4) == (src >> 4)) thr = nt;
+  }
+  return thr;
+}
+
+// FLAGS: bit0 TD predicate, bit1 GC and/or coverage predicates, bit2 masks, bit3 top-k
+template <int FLAGS>
+__global__ void __launch_bounds__(THREADS, 1) pairs_kernel(const __grid_constant__ CUtensorMap tmap, const Params P) {
+  constexpr bool F_TD = (FLAGS & 1) != 0, F_GCCOV = (FLAGS & 2) != 0, F_MASK = (FLAGS & 4) != 0, F_TOPK = (FLAGS & 8) != 0;
+  extern __shared__ uint8_t smem_raw[];
+  SmemLayout& sm = *reinterpret_cast<SmemLayout*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t n = P.n;
+  const int64_t n_rows = P.row1 - P.row0;
+  const int n_rt = (int)((n_rows + TILE - 1) / TILE);
+  const int n_ct = (int)((n + TILE - 1) / TILE);
+
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], COMPUTE_WARPS); }
+    mbar_init(&sm.a_full, 1);
+    mbar_init(&sm.a_empty, COMPUTE_WARPS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // ================= compute warps =================
+  const int ty = lane >> 4, tx = lane & 15;
+  const int k = P.k;
+  const bool has_td = F_TD, has_gc = F_GCCOV && P.gc != nullptr, has_cov = F_GCCOV && P.cov != nullptr;
+  const bool want_cnt = P.count != nullptr || P.neighbour_bp != nullptr;
+  uint32_t q = 0, rt_iter = 0;
+  // B chunks of this CTA form one sequence over all its row sweeps: chunk pq is K-chunk pq%5 of
+  // column tile (pq/5) % n_ct; it lands in ring stage pq % NSTAGE
+  const uint32_t my_rt = (n_rt > (int)blockIdx.x) ? (uint32_t)((n_rt - 1 - (int)blockIdx.x) / (int)gridDim.x + 1) : 0u;
+  const uint32_t total_chunks = my_rt * (uint32_t)n_ct * NKC;
+  auto issue_b = [&](uint32_t pq) {
+    const uint32_t st = pq % NSTAGE;
+    if (pq >= NSTAGE) mbar_wait(&sm.empty[st], ((pq / NSTAGE) - 1) & 1);
+    mbar_arrive_expect_tx(&sm.full[st], CHUNK_BYTES);
+    tma_load_2d(&sm.b[st][0][0], &tmap, (int32_t)((pq % NKC) * KCH), (int32_t)(((pq / NKC) % (uint32_t)n_ct) * TILE), &sm.full[st]);
+  };
+
+  for (int rt = blockIdx.x; rt < n_rt; rt += gridDim.x, ++rt_iter) {
+    const int64_t row_base = P.row0 + (int64_t)rt * TILE;
+    // stage row scalars and reset the top-k lists of this warp's 16 rows
+    for (int r = lane; r < 16; r += 32) {
+      const int lr = warp * 16 + r;
+      const int64_t gr = row_base + lr;
+      RowScalars rs;
+      rs.len = 0; rs.tdb = 0.f; rs.gcm = 0; rs.gcl = 0; rs.covl = 0; rs.pad = 0; rs.gc = 0.0; rs.cov = 0.0;
+      if (gr < n) {
+        rs.len = P.length[gr];
+        if (has_td) rs.tdb = P.td_bound[gr];
+        if (has_gc) { rs.gc = P.gc[gr]; rs.gcm = P.gc_mbin[gr]; rs.gcl = P.gc_lbin[gr]; }
+        if (has_cov) { rs.cov = P.cov[gr]; rs.covl = P.cov_lbin[gr]; }
+      }
+      sm.rows[lr] = rs;
+    }
+    for (int r = 0; r < 16; ++r) {
+      sm.list_d[warp * 16 + r][lane] = INFINITY;
+      sm.list_j[warp * 16 + r][lane] = INT_MAX;
+    }
+    __syncwarp();
+
+    float thr[8];
+    int32_t cnt[8];
+    long long bp[8];
+    #pragma unroll
+    for (int i = 0; i < 8; ++i) { thr[i] = INFINITY; cnt[i] = 0; bp[i] = 0; }
+
+    // thread 0 doubles as the TMA producer: A tile of this sweep + the first PREFETCH B chunks
+    if (tid == 0) {
+      if (rt_iter > 0) mbar_wait(&sm.a_empty, (rt_iter - 1) & 1);
+      mbar_arrive_expect_tx(&sm.a_full, NKC * CHUNK_BYTES);
+      for (int kc = 0; kc < NKC; ++kc) tma_load_2d(&sm.a[kc][0][0], &tmap, kc * KCH, (int32_t)row_base, &sm.a_full);
+      if (rt_iter == 0)
+        for (uint32_t pq = 0; pq < (uint32_t)PREFETCH && pq < total_chunks; ++pq) issue_b(pq);
+    }
+    mbar_wait(&sm.a_full, rt_iter & 1);
+
+    for (int ct = 0; ct < n_ct; ++ct) {
+      float2 acc[8][8];
+      #pragma unroll
+      for (int i = 0; i < 8; ++i)
+        #pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = make_float2(0.f, 0.f);
+
+      for (int kc = 0; kc < NKC; ++kc, ++q) {
+        const uint32_t st = q % NSTAGE;
+        if (tid == 0 && q + PREFETCH < total_chunks) issue_b(q + PREFETCH);
+        mbar_wait(&sm.full[st], (q / NSTAGE) & 1);
+        const float* ap = &sm.a[kc][warp * 16 + ty][0];
+        const float* bp_ = &sm.b[st][tx][0];
+        #pragma unroll
+        for (int k4 = 0; k4 < KCH / 4; ++k4) {
+          float4 av[8];
+          #pragma unroll
+          for (int i = 0; i < 8; ++i) av[i] = *reinterpret_cast<const float4*>(ap + (2 * i) * KCH + k4 * 4);
+          #pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 bv = *reinterpret_cast<const float4*>(bp_ + (16 * j) * KCH + k4 * 4);
+            #pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              acc[i][j] = absdiff_acc(acc[i][j], make_float2(av[i].x, av[i].y), make_float2(bv.x, bv.y));
+              acc[i][j] = absdiff_acc(acc[i][j], make_float2(av[i].z, av[i].w), make_float2(bv.z, bv.w));
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.empty[st]);
+      }
+
+      // ---------------- epilogue of this column tile ----------------
+      const int64_t col_base = (int64_t)ct * TILE;
+      #pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int64_t cj = col_base + tx + 16 * j;
+        const bool col_ok = cj < n;
+        int32_t len_j = 0; float tdb_j = 0.f;
+        double gc_j = 0.0, cov_j = 0.0; int32_t gcm_j = 0, gcl_j = 0, covl_j = 0;
+        if (col_ok) {
+          len_j = __ldg(P.length + cj);
+          if (has_td) tdb_j = __ldg(P.td_bound + cj);
+          if (has_gc) { gc_j = __ldg(P.gc + cj); gcm_j = __ldg(P.gc_mbin + cj); gcl_j = __ldg(P.gc_lbin + cj); }
+          if (has_cov) { cov_j = __ldg(P.cov + cj); covl_j = __ldg(P.cov_lbin + cj); }
+        }
+        #pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int lr = warp * 16 + 2 * i + ty;
+          const int64_t gi = row_base + lr;
+          const RowScalars& rs = sm.rows[lr];
+          const float d = acc[i][j].x + acc[i][j].y;
+          const bool i_core = rs.len > len_j;
+          bool p_td = true, p_gc = true, p_cov = true;
+          if (has_td) p_td = d < (i_core ? tdb_j : rs.tdb);
+          if (has_gc) {
+            const int m = i_core ? rs.gcm : gcm_j, l = i_core ? gcl_j : rs.gcl;
+            const double lo = __ldg(P.gc_lo + m * P.gc_nl + l), hi = __ldg(P.gc_hi + m * P.gc_nl + l);
+            const double diff = i_core ? (gc_j - rs.gc) : (rs.gc - gc_j);
+            p_gc = diff >= lo && diff <= hi;
+          }
+          if (has_cov) {
+            const double cc = i_core ? rs.cov : cov_j, cu = i_core ? cov_j : rs.cov;
+            const int l = i_core ? covl_j : rs.covl;
+            const double eff = cc > 0 ? cc : 0.1;
+            const double diff = (cu - eff) * 100.0 / eff;
+            p_cov = diff >= __ldg(P.cov_lo + l) && diff <= __ldg(P.cov_hi + l);
+          }
+          p_td = p_td && col_ok; p_gc = p_gc && col_ok; p_cov = p_cov && col_ok;
+          const bool all = p_td && p_gc && p_cov;
+          if (want_cnt && all) { cnt[i] += 1; bp[i] += len_j; }
+
+          if (F_MASK) {
+            // one ballot = 16 columns of row (ty=0) in the low half, of row (ty=1) in the high half
+            const uint32_t bt = __ballot_sync(0xffffffffu, p_td);
+            const uint32_t bg = __ballot_sync(0xffffffffu, p_gc);
+            const uint32_t bc = __ballot_sync(0xffffffffu, p_cov);
+            if (tx == 0 && gi < P.row1) {
+              const int64_t w = (col_base >> 5) + (j >> 1);
+              if (w < P.mask_words) {
+                const int sh = 16 * (j & 1);
+                const size_t o = (size_t)(gi - P.row0) * P.mask_words + w;
+                // the two 16-bit halves of a word are written by the same lane in consecutive j
+                if (P.td_mask) { uint32_t v = ((bt >> (16 * ty)) & 0xffffu) << sh; if (sh) P.td_mask[o] |= v; else P.td_mask[o] = v; }
+                if (P.gc_mask && has_gc) { uint32_t v = ((bg >> (16 * ty)) & 0xffffu) << sh; if (sh) P.gc_mask[o] |= v; else P.gc_mask[o] = v; }
+                if (P.cov_mask && has_cov) { uint32_t v = ((bc >> (16 * ty)) & 0xffffu) << sh; if (sh) P.cov_mask[o] |= v; else P.cov_mask[o] = v; }
+              }
+            }
+          }
+
+          if (F_TOPK) {
+            bool cand = col_ok && (cj != gi) && (d <= thr[i]);
+            if (P.topk_filter & 1) cand = cand && p_td;
+            if (P.topk_filter & 2) cand = cand && p_gc;
+            if (P.topk_filter & 4) cand = cand && p_cov;
+            const uint32_t m = __ballot_sync(0xffffffffu, cand);
+            if (m) thr[i] = insert_candidates(sm, m, d, thr[i], (int32_t)(col_base + 16 * j), warp * 16 + 2 * i, k, lane);
+          }
+        }
+      }
+    }  // column tiles
+
+    // this warp is done with the A tile of this row sweep
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sm.a_empty);
+
+    // ---------------- per-row outputs ----------------
+    #pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int32_t c = cnt[i];
+      long long b = bp[i];
+      #pragma unroll
+      for (int dlt = 8; dlt > 0; dlt >>= 1) {
+        c += __shfl_xor_sync(0xffffffffu, c, dlt);
+        b += __shfl_xor_sync(0xffffffffu, b, dlt);
+      }
+      const int64_t gi = row_base + warp * 16 + 2 * i + ty;
+      if (tx == 0 && gi < P.row1) {
+        if (P.count) P.count[gi - P.row0] = c;
+        if (P.neighbour_bp) P.neighbour_bp[gi - P.row0] = b;
+      }
+    }
+    if (F_TOPK) {
+      for (int r = 0; r < 16; ++r) {
+        const int lr = warp * 16 + r;
+        const int64_t gi = row_base + lr;
+        if (gi < P.row1 && lane < k) {
+          const int32_t ej = sm.list_j[lr][lane];
+          if (P.knn_idx) P.knn_idx[(gi - P.row0) * k + lane] = (ej == INT_MAX) ? -1 : ej;
+          if (P.knn_dist) P.knn_dist[(gi - P.row0) * k + lane] = sm.list_d[lr][lane];
+        }
+      }
+    }
+    __syncwarp();
+  }  // row tiles
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int get_encode_fn(EncodeTiledFn* fn) {
+  static EncodeTiledFn cached = nullptr;
+  if (!cached) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    DBB_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+    if (qres != cudaDriverEntryPointSuccess || !p) {
+      dbb::set_error("cuTensorMapEncodeTiled is not available in this driver");
+      return DBB_ERR_CUDA;
+    }
+    cached = (EncodeTiledFn)p;
+  }
+  *fn = cached;
+  return DBB_OK;
+}
+
+template <int FLAGS>
+int launch_one(unsigned grid, size_t smem, cudaStream_t st, const CUtensorMap& tmap, const Params& P) {
+  DBB_CUDA_TRY(cudaFuncSetAttribute(pairs_kernel<FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  pairs_kernel<FLAGS><<<grid, THREADS, smem, st>>>(tmap, P);
+  DBB_CUDA_TRY(cudaGetLastError());
+  return DBB_OK;
+}
+
+int launch_pairs(int flags, unsigned grid, size_t smem, cudaStream_t st, const CUtensorMap& tmap, const Params& P) {
+  switch (flags) {
+#define DBB_CASE(F) case F: return launch_one<F>(grid, smem, st, tmap, P);
+    DBB_CASE(0) DBB_CASE(1) DBB_CASE(2) DBB_CASE(3) DBB_CASE(4) DBB_CASE(5) DBB_CASE(6) DBB_CASE(7)
+    DBB_CASE(8) DBB_CASE(9) DBB_CASE(10) DBB_CASE(11) DBB_CASE(12) DBB_CASE(13) DBB_CASE(14) DBB_CASE(15)
+#undef DBB_CASE
+  }
+  dbb::set_error("bad pairs flags");
+  return DBB_ERR_INVALID;
+}
+
+}  // namespace
+
+DBB_EXPORT int64_t dbb_pairs_scratch_bytes(int64_t, int64_t, int32_t) { return 0; }
+
+DBB_EXPORT int dbb_pairs_dev(const dbb_pairs_input* in, int64_t row0, int64_t row1, const dbb_pairs_output* out,
+                             void* stream) {
+  DBB_REQUIRE(in && out, "NULL argument struct");
+  DBB_REQUIRE(in->n >= 0 && row0 >= 0 && row1 >= row0 && row1 <= in->n, "bad row range");
+  if (row1 == row0 || in->n == 0) return DBB_OK;
+  DBB_REQUIRE(in->n < (1ll << 31) - TILE, "n too large for int32 indices");
+  DBB_REQUIRE(in->sig && in->length, "sig/length are required");
+  DBB_REQUIRE(((uintptr_t)in->sig & 15) == 0, "sig must be 16-byte aligned");
+  DBB_REQUIRE(out->k >= 0 && out->k <= DBB_MAX_K, "k out of range (0..32)");
+  DBB_REQUIRE(!in->gc || (in->gc_mbin && in->gc_lbin && in->gc_lo && in->gc_hi && in->gc_nl > 0), "incomplete GC inputs");
+  DBB_REQUIRE(!in->cov || (in->cov_lbin && in->cov_lo && in->cov_hi), "incomplete coverage inputs");
+  const bool masks = out->td_mask || out->gc_mask || out->cov_mask;
+  DBB_REQUIRE(!masks || out->mask_words * 32 >= in->n, "mask_words too small");
+  DBB_REQUIRE(!out->td_mask || in->td_bound, "td_mask requested without td_bound");
+
+  EncodeTiledFn encode;
+  int rc = get_encode_fn(&encode);
+  if (rc != DBB_OK) return rc;
+  CUtensorMap tmap;
+  cuuint64_t gdim[2] = {(cuuint64_t)DBB_SIG_STRIDE, (cuuint64_t)in->n};
+  cuuint64_t gstr[1] = {(cuuint64_t)DBB_SIG_STRIDE * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)KCH, (cuuint32_t)TILE};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)in->sig, gdim, gstr, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) { dbb::set_error("cuTensorMapEncodeTiled failed (%d)", (int)cr); return DBB_ERR_CUDA; }
+
+  Params P;
+  P.n = in->n; P.row0 = row0; P.row1 = row1;
+  P.length = in->length; P.td_bound = in->td_bound;
+  P.gc = in->gc; P.gc_mbin = in->gc_mbin; P.gc_lbin = in->gc_lbin; P.gc_lo = in->gc_lo; P.gc_hi = in->gc_hi; P.gc_nl = in->gc_nl;
+  P.cov = in->cov; P.cov_lbin = in->cov_lbin; P.cov_lo = in->cov_lo; P.cov_hi = in->cov_hi;
+  P.k = out->k; P.topk_filter = out->topk_filter;
+  P.knn_idx = out->knn_idx; P.knn_dist = out->knn_dist; P.count = out->count; P.neighbour_bp = out->neighbour_bp;
+  P.td_mask = out->td_mask; P.gc_mask = out->gc_mask; P.cov_mask = out->cov_mask; P.mask_words = out->mask_words;
+
+  int dev = 0, sms = 0;
+  DBB_CUDA_TRY(cudaGetDevice(&dev));
+  DBB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const size_t smem = sizeof(SmemLayout) + 128;
+  const int64_t n_rt = (row1 - row0 + TILE - 1) / TILE;
+  const unsigned grid = (unsigned)std::min<int64_t>(n_rt, sms);
+  const int flags = (in->td_bound ? 1 : 0) | ((in->gc || in->cov) ? 2 : 0) | (masks ? 4 : 0) | (out->k > 0 ? 8 : 0);
+  return launch_pairs(flags, grid, smem, (cudaStream_t)stream, tmap, P);
+}

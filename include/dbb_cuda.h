@@ -1,0 +1,158 @@
+/*
+ * dbb_cuda.h -- C ABI of libdbbcuda.so: DBB's data-parallel hot path on NVIDIA B200 (sm_100a).
+ *
+ * The reference (donovan-h-parks/DBB) is pure Python with no FFI layer; the "plugin boundary" for this
+ * path is the method surface of four modules.  Each entry point below names the reference code it
+ * replaces (file:line into /root/reference/dbb).  The Python mirror of those modules lives in
+ * dbb_b200/ and binds these symbols with ctypes (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - every function returns int: DBB_OK (0) or a negative DBB_ERR_*; never throws, never aborts;
+ *     dbb_last_error() returns a thread-local message for the last failure.
+ *   - "_dev" functions take DEVICE pointers and a cudaStream_t (as void*; NULL = default stream),
+ *     enqueue work on the CURRENT device and return without synchronising.
+ *   - "_host" functions take HOST pointers, do their own H2D/D2H and return when results are in the
+ *     output buffers.  The caller owns every buffer passed in; the library owns only its scratch.
+ *   - no CPU fallback exists: without a CUDA device every compute entry point returns DBB_ERR_CUDA.
+ *
+ * Packed sequence layout: a scaffold of L bases occupies ceil(L/64) BLOCKS.
+ *   codes plane : 16 bytes per block = 4 little-endian uint32 words, word w holds bases 16w..16w+15,
+ *                 2 bits per base (A=0 C=1 G=2 T=3), FIRST base in the MOST significant bits.
+ *   valid plane :  8 bytes per block = one uint64, bit (63-p) set iff base p of the block is one of
+ *                 the four UPPERCASE letters A C G T (anything else, and the padding past the end of
+ *                 the scaffold, is invalid -- genomicSignatures.py:139-144 skips such windows).
+ *   blk_off[s]  : first block of scaffold s; blk_off[n_seq] = total blocks.  Windows never span
+ *                 scaffolds.
+ */
+#ifndef DBB_CUDA_H
+#define DBB_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DBB_NUM_KMERS 136      /* canonical tetramers, genomicSignatures.py:44-72 */
+#define DBB_SIG_STRIDE 140     /* floats per row of the padded signature matrix used by stage 2 */
+#define DBB_BLOCK_BASES 64
+#define DBB_MAX_K 32
+
+enum {
+  DBB_OK = 0,
+  DBB_ERR_INVALID = -1,        /* bad argument */
+  DBB_ERR_CUDA = -2,           /* CUDA runtime/driver failure (message in dbb_last_error) */
+  DBB_ERR_NOMEM = -3,
+  DBB_ERR_UNSUPPORTED = -4     /* e.g. K != 4, k > DBB_MAX_K, device is not sm_100 */
+};
+
+const char* dbb_last_error(void);
+int dbb_version(void);
+/* device facts for roofline arithmetic: SM count, compute capability, free/total bytes */
+int dbb_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* free_bytes, int64_t* total_bytes);
+
+/* ---- canonical tetramer table: genomicSignatures.py:35-84 (__init__, __makeKmerColNames,
+ * ---- __lexicographicallyLowest, __revComp) ------------------------------------------------------ */
+/* lut256[code] = canonical column of the 4-mer with 2-bit code `code` (first base most significant) */
+int dbb_kmer_lut(uint8_t* lut256);
+/* names: 136 NUL-terminated 4-letter names, 5 bytes each, in column order (canonicalKmerOrder, :128) */
+int dbb_kmer_names(char* names680);
+
+/* ---- stage 1: tetranucleotide signatures -- genomicSignatures.py:134-150 (seqSignature) and the
+ * ---- fan-out of :152-181 (calculate) ---------------------------------------------------------------- */
+int64_t dbb_packed_blocks(int64_t seq_len);
+/* blk_off[0..n_seq] from lengths (host helper) */
+int dbb_block_offsets(const int64_t* seq_len, int64_t n_seq, int64_t* blk_off);
+
+/* ASCII -> packed planes.  d_seq_off[n_seq+1] are byte offsets of each scaffold in d_ascii. */
+int dbb_pack_ascii_dev(const uint8_t* d_ascii, const int64_t* d_seq_off, const int64_t* d_blk_off,
+                       int64_t n_seq, int64_t total_blocks, void* d_codes, void* d_valid, void* stream);
+
+/* A count plan = the device-resident work list (chunks of scaffolds, 16 bytes of metadata each)
+ * derived from HOST block offsets.  Build once per batch, run many times. */
+typedef struct dbb_count_plan dbb_count_plan;
+int dbb_count_plan_create(const int64_t* h_blk_off, int64_t n_seq, dbb_count_plan** plan);
+int dbb_count_plan_destroy(dbb_count_plan* plan);
+/* number of kernels one dbb_tetra_count_dev call launches (for launch accounting) */
+int dbb_count_plan_launches(const dbb_count_plan* plan);
+
+/* packed planes -> counts uint32[n_seq][136] (bit-exact) and freq float[n_seq][freq_stride]
+ * (freq = count / sum(count); all-zero counts give NaN as genomicSignatures.py:147-148 does;
+ * freq_stride >= 136, columns 136..freq_stride-1 are written as 0).  Either output may be NULL. */
+int dbb_tetra_count_dev(dbb_count_plan* plan, const void* d_codes, const void* d_valid,
+                        uint32_t* d_counts, float* d_freq, int64_t freq_stride, void* stream);
+
+/* Whole stage 1 from host memory: ASCII in, counts/freq out (freq is [n_seq][136], dense).
+ * Replaces the per-sequence loop of genomicSignatures.py:152-181. */
+int dbb_tetra_signatures_host(const uint8_t* ascii, const int64_t* seq_off, int64_t n_seq,
+                              uint32_t* counts, float* freq);
+
+/* ---- stage 2: all-pairs tetranucleotide distance, neighbour predicates and fused top-k ------------
+ * tdNeighbours.py:41-51, gcNeighbours.py:43-52, coverageNeighbours.py:41-50 with the bounds of
+ * distributions.py:75-127 resolved ONCE PER SCAFFOLD on the host (the algebraic restatement in
+ * SURVEY.md section 8a): every per-pair bound depends only on per-scaffold scalars.              */
+typedef struct {
+  int64_t n;                   /* scaffolds (columns) */
+  const float* sig;            /* [n][DBB_SIG_STRIDE] float32 frequencies, cols 136..139 zero */
+  const int32_t* length;       /* [n] */
+  /* TD predicate (tdNeighbours.py:43-51): pass iff L1 < bound of the SHORTER scaffold (ties -> i).
+   * td_bound[s] = tdDist[nearest(len_s or fixedSeqLen)][tdKey]; NULL disables the predicate. */
+  const float* td_bound;       /* [n] or NULL */
+  /* GC predicate (gcNeighbours.py:44-52, distributions.py:75-93); gc == NULL disables it. */
+  const double* gc;            /* [n] */
+  const int32_t* gc_mbin;      /* [n] nearest mean-GC key index of the scaffold (used when it is the core) */
+  const int32_t* gc_lbin;      /* [n] nearest length key index (used when it is the unbinned one) */
+  const double* gc_lo;         /* [gc_nm][gc_nl] lower bounds at the lower percentile key */
+  const double* gc_hi;         /* [gc_nm][gc_nl] */
+  int32_t gc_nm, gc_nl;
+  /* coverage predicate (coverageNeighbours.py:42-50, distributions.py:106-127); cov == NULL disables */
+  const double* cov;           /* [n] */
+  const int32_t* cov_lbin;     /* [n] */
+  const double* cov_lo;        /* [cov_nl] */
+  const double* cov_hi;        /* [cov_nl] */
+  int32_t cov_nl;
+} dbb_pairs_input;
+
+typedef struct {
+  /* top-k (NEW output, not in the reference): for row i the candidates are j != i that pass the
+   * predicates selected by topk_filter, ordered by (distance asc, j asc).  k == 0 disables. */
+  int32_t k;                   /* 0..DBB_MAX_K */
+  int32_t topk_filter;         /* bit0: TD, bit1: GC, bit2: coverage must pass to be a candidate */
+  int32_t* knn_idx;            /* [rows][k] padded with -1, or NULL */
+  float* knn_dist;             /* [rows][k] padded with +inf, or NULL */
+  /* neighbourhood of the intersection of all ENABLED predicates, j == i included, i.e. what
+   * greedy.py:407-417 derives from the three masks */
+  int32_t* count;              /* [rows] or NULL */
+  int64_t* neighbour_bp;       /* [rows] sum of length[j] over that intersection, or NULL */
+  /* bit masks, one bit per column, row stride mask_words uint32 (bit j%32 of word j/32):
+   * the dense 0/1 rows the reference stores in .tdNeighbours / .gcNeighbours / .covNeighbours */
+  uint32_t* td_mask;           /* [rows][mask_words] or NULL */
+  uint32_t* gc_mask;
+  uint32_t* cov_mask;
+  int64_t mask_words;
+} dbb_pairs_output;
+
+/* rows [row0, row1) of the all-pairs problem against all n columns.  All pointers are device
+ * pointers.  Enqueues on `stream`. */
+int dbb_pairs_dev(const dbb_pairs_input* in, int64_t row0, int64_t row1, const dbb_pairs_output* out,
+                  void* stream);
+/* bytes of device scratch dbb_pairs_dev needs internally for (n, rows, k) -- informational */
+int64_t dbb_pairs_scratch_bytes(int64_t n, int64_t rows, int32_t k);
+/* same with HOST pointers everywhere (sig is dense [n][136] float32 on the host) */
+int dbb_pairs_host(const dbb_pairs_input* in_host, int64_t row0, int64_t row1,
+                   const dbb_pairs_output* out_host);
+
+/* dense [n][136] -> padded [n][DBB_SIG_STRIDE] on device (used after the all-gather) */
+int dbb_pad_signatures_dev(const float* d_dense, int64_t n, float* d_padded, void* stream);
+
+/* ---- synthetic input (benchmark/test support; dbb_b200/synthetic.py is the host twin) ------------ */
+int dbb_synth_ascii_dev(uint64_t seed, int64_t n_seq, const int64_t* d_seq_off, const int64_t* d_blk_off,
+                        int64_t total_blocks, const int32_t* d_genome, const uint32_t* d_cum /* [G][64][3] */,
+                        const int64_t* d_n_start, const int64_t* d_n_len, const int64_t* d_lc_start,
+                        const int64_t* d_lc_len, uint8_t* d_ascii, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DBB_CUDA_H */

@@ -139,6 +139,13 @@ def main():
         neigh['cov_' + tag] = run_rows(CoverageNeighbours(fixed), '_CoverageNeighbours__workerThread', contigs, dC)
     dist = np.array([[gs.distance(a.tetraSig, b.tetraSig) for b in contigs] for a in contigs])
 
+    # the reference's td_dist.txt re-encoded as arrays (exact float64 values) for dbb_b200/data
+    lens = sorted(tdDist.keys())
+    pcts = sorted(tdDist[lens[0]].keys())
+    np.savez_compressed(os.path.join(HERE, '..', '..', 'dbb_b200', 'data', 'td_dist.npz'),
+                        lengths=np.array(lens, dtype=np.int64), percentiles=np.array(pcts, dtype=np.float64),
+                        values=np.array([[tdDist[l][p] for p in pcts] for l in lens], dtype=np.float64))
+
     with open(os.path.join(HERE, 'ref_table.json'), 'w') as f:
         json.dump(table, f, indent=0, sort_keys=True)
     with open(os.path.join(HERE, 'ref_kat_seqs.json'), 'w') as f:

@@ -1,0 +1,129 @@
+"""Parity of stage 2 (all-pairs distance, neighbour predicates, fused top-k) on the GPU against the oracle
+and the golden rows produced by the reference's own __workerThread loops.  GC / coverage masks: exact.
+TD mask: exact outside |d64 - bound| <= 2e-6.  Distances: |d32 - d64| <= 2e-6."""
+import numpy as np
+import pytest
+
+from oracle import dbb_oracle as O
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+CASES = (('fixedNone_p80', None, 80), ('fixed10000_p80', 10000, 80), ('fixedNone_p99', None, 99))
+
+
+def _golden_contigs():
+    nb = util.golden_npz('ref_neighbours.npz')
+    cs = [O.Contig('c%d' % i, int(nb['length'][i]), float(nb['GC'][i]), float(nb['coverage'][i]), nb['tetraSig'][i])
+          for i in range(len(nb['length']))]
+    return nb, cs
+
+
+def _dists():
+    from dbb_b200 import synthetic
+    from dbb_b200.data import load_td_dist
+    return load_td_dist(), synthetic.synthetic_gc_dist(), synthetic.synthetic_cov_dist(seed=7)
+
+
+@pytest.mark.parametrize('tag,fixed,per', CASES)
+def test_golden_rows_through_dropin_classes(tag, fixed, per):
+    from dbb_b200.tdNeighbours import TdNeighbours
+    from dbb_b200.gcNeighbours import GcNeighbours
+    from dbb_b200.coverageNeighbours import CoverageNeighbours
+    nb, cs = _golden_contigs()
+    td, gcd, cvd = _dists()
+    assert TdNeighbours(fixed).run(cs, td, per, 4) is None
+    GcNeighbours(fixed).run(cs, gcd, per, 4)
+    CoverageNeighbours(fixed).run(cs, cvd, per, 4)
+    got_td = np.array([c.tdNeighbours for c in cs]); got_gc = np.array([c.gcNeighbours for c in cs])
+    got_cov = np.array([c.covNeighbours for c in cs])
+    assert got_td.dtype == np.float64 and got_td.shape == nb['td_' + tag].shape
+    assert np.array_equal(got_gc, nb['gc_' + tag])
+    assert np.array_equal(got_cov, nb['cov_' + tag])
+    tables = O.DistTables(tdDist=td, tdDistPer=per)
+    bound = O.td_bound_rows_np(nb['length'], list(range(len(cs))), tables, fixed)
+    with np.errstate(invalid='ignore'):
+        util.check_mask_against_oracle(got_td, nb['td_' + tag], nb['distance'], bound)
+    # the expressions greedy.py:409-414 applies to the attributes
+    i = 3
+    assert np.array_equal(np.where(cs[i].tdNeighbours == 1)[0], np.where(got_td[i] == 1)[0])
+
+
+def _metagenome(seed, n, gmax=30000):
+    from dbb_b200 import synthetic
+    from dbb_b200.genomicSignatures import GenomicSignatures
+    meta = synthetic.make_metagenome(seed=seed, n_scaffolds=n, min_len=1000, max_len=gmax, n_genomes=6)
+    seqs = synthetic.generate_sequences(meta)
+    counts, _ = GenomicSignatures(4, 1).signatures(seqs, want_freq=False)
+    sig64 = counts.astype(np.float64) / counts.sum(axis=1, keepdims=True)
+    return meta, sig64
+
+
+def test_masks_counts_topk_vs_oracle_all_predicates():
+    from dbb_b200 import _pairs
+    from dbb_b200.distributions import PairTables
+    meta, sig64 = _metagenome(21, 700)
+    sig64[17] = np.nan                                    # NaN signature: neighbour of nobody
+    meta.coverage[5] = 0.0
+    td, gcd, cvd = _dists()
+    n = meta.n_scaffolds
+    rows = list(range(n))
+    for fixed in (None, 10000):
+        tables = PairTables(meta.length, GC=meta.gc_obs, coverage=meta.coverage, tdDist=td, tdDistPer=80, gcDist=gcd,
+                            gcDistPer=80, covDist=cvd, covDistPer=80, fixedSeqLen=fixed)
+        res = _pairs.run_pairs_host(sig64, tables, k=20, topk_filter=_pairs.FILTER_GC | _pairs.FILTER_COV,
+                                    want_count=True, want_td_mask=True, want_gc_mask=True, want_cov_mask=True)
+        ot = O.DistTables(gcd, 80, td, 80, cvd, 80)
+        with np.errstate(invalid='ignore'):
+            d64 = O.l1_rows_np(sig64.astype(np.float32).astype(np.float64), rows)
+            o_td = O.td_rows_np(sig64.astype(np.float32).astype(np.float64), meta.length, rows, ot, fixed)
+        o_gc = O.gc_rows_np(meta.length, meta.gc_obs, rows, ot, fixed)
+        o_cov = O.cov_rows_np(meta.length, meta.coverage, rows, ot, fixed)
+        g_td, g_gc, g_cov = (util.unpack_mask(res[k_], n) for k_ in ('td_mask', 'gc_mask', 'cov_mask'))
+        assert np.array_equal(g_gc, o_gc) and np.array_equal(g_cov, o_cov)
+        bound = O.td_bound_rows_np(meta.length, rows, ot, fixed)
+        with np.errstate(invalid='ignore'):
+            flips = util.check_mask_against_oracle(g_td, o_td, d64, bound)
+        allm = (g_td & g_gc & g_cov).astype(bool)
+        assert np.array_equal(res['count'], allm.sum(axis=1))
+        assert np.array_equal(res['neighbour_bp'], (allm * meta.length[None, :]).sum(axis=1))
+        util.check_topk(res['idx'], res['dist'].astype(np.float64), d64, rows, 20, allowed=(o_gc * o_cov))
+        assert flips <= 2
+
+
+def test_plain_knn_and_row_block_invariance():
+    """k-NN without predicates; results for a row block are identical to the same rows of the full run
+    (what makes the multi-GPU row sharding exact)."""
+    from dbb_b200 import _pairs
+    from dbb_b200.distributions import PairTables
+    meta, sig64 = _metagenome(22, 1000, gmax=20000)
+    n = meta.n_scaffolds
+    td = _dists()[0]
+    tables = PairTables(meta.length, tdDist=td, tdDistPer=80)
+    full = _pairs.run_pairs_host(sig64, tables, k=20, want_count=True)
+    d64 = O.l1_rows_np(sig64.astype(np.float32).astype(np.float64), list(range(n)))
+    util.check_topk(full['idx'], full['dist'].astype(np.float64), d64, list(range(n)), 20)
+    for r0, r1 in ((0, 130), (130, 515), (515, n)):
+        part = _pairs.run_pairs_host(sig64, tables, k=20, want_count=True, row0=r0, row1=r1)
+        for key in ('idx', 'dist', 'count', 'neighbour_bp'):
+            assert np.array_equal(part[key], full[key][r0:r1]), key
+    for k in (1, 5, 32):
+        r = _pairs.run_pairs_host(sig64, tables, k=k)
+        util.check_topk(r['idx'], r['dist'].astype(np.float64), d64, list(range(n)), k)
+
+
+def test_small_and_degenerate_inputs():
+    from dbb_b200 import _pairs
+    from dbb_b200.distributions import PairTables
+    td = _dists()[0]
+    rng = np.random.RandomState(9)
+    for n in (1, 2, 19, 128, 129):
+        sig = rng.dirichlet(np.ones(136), n)
+        length = rng.randint(1000, 50000, n)
+        tables = PairTables(length, tdDist=td, tdDistPer=80)
+        r = _pairs.run_pairs_host(sig, tables, k=20, want_count=True, want_td_mask=True)
+        d64 = O.l1_rows_np(sig.astype(np.float32).astype(np.float64), list(range(n)))
+        util.check_topk(r['idx'], r['dist'].astype(np.float64), d64, list(range(n)), 20)
+        m = util.unpack_mask(r['td_mask'], n)
+        assert (np.diag(m) == 1).all()                     # i == j is always a TD neighbour (0 < bound)
+        assert np.array_equal(r['count'], m.sum(axis=1))
