@@ -1,0 +1,84 @@
+"""CPU: the C-ABI library loads without a GPU, exports every symbol include/dbb_cuda.h declares, its
+GPU-free entry points work, and the compute entry points FAIL LOUDLY (no CPU fallback) when no CUDA device
+is present."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from dbb_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, 'include', 'dbb_cuda.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(dbb_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_library_exports_every_declared_symbol():
+    assert os.path.exists(_lib.LIB_PATH), 'run python -m dbb_b200.build'
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    names = _declared()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(L, n), 'missing export ' + n
+    assert sorted(_lib.SIGNATURES) == names, 'ctypes table and header disagree'
+
+
+def test_table_entry_points_without_gpu():
+    from oracle import dbb_oracle as O
+    names, lut = _lib.kmer_table()
+    assert names == O.KMER_COLS
+    assert np.array_equal(lut, O.code_lut256())
+    L = _lib.lib()
+    assert L.dbb_version() >= 100
+    assert [L.dbb_packed_blocks(x) for x in (0, 1, 63, 64, 65, 128)] == [0, 1, 1, 1, 2, 2]
+    lens = np.array([0, 1, 64, 65, 1000], dtype=np.int64)
+    off = np.zeros(6, dtype=np.int64)
+    _lib.check(L.dbb_block_offsets(_lib.ptr(lens), 5, _lib.ptr(off)))
+    assert off.tolist() == [0, 0, 1, 2, 4, 20]
+    bad = np.array([5, -1], dtype=np.int64)
+    assert L.dbb_block_offsets(_lib.ptr(bad), 2, _lib.ptr(off)) == -1 and b'negative' in L.dbb_last_error()
+
+
+def test_dropin_surface_and_k_restriction():
+    from dbb_b200.genomicSignatures import GenomicSignatures
+    import pickle
+    g = GenomicSignatures(4, 8)
+    assert g.K == 4 and g.totalThreads == 8 and g.numKmers() == 136 and g.canonicalKmerOrder()[0] == 'AAAA'
+    assert 'ACGT'.translate(g.compl) == 'TGCA' and len(g.kmerToCanonicalIndex) == 256
+    assert g.kmerToCanonicalIndex['TTTT'] == g.kmerToCanonicalIndex['AAAA'] == 0
+    pickle.loads(pickle.dumps(g))                                   # preprocess.py:395-413 forks/pickles it
+    a, b = np.full(136, 1 / 136.0), np.zeros(136); b[0] = 1.0
+    assert abs(g.distance(a, b) - (2 - 2 / 136.0)) < 1e-12
+    with pytest.raises(NotImplementedError):
+        GenomicSignatures(5, 1)
+    for mod, cls in (('tdNeighbours', 'TdNeighbours'), ('gcNeighbours', 'GcNeighbours'), ('coverageNeighbours', 'CoverageNeighbours')):
+        m = __import__('dbb_b200.' + mod, fromlist=[cls])
+        obj = getattr(m, cls)(10000)
+        assert obj.fixedSeqLen == 10000 and hasattr(obj, 'run') and hasattr(obj, 'logger')
+
+
+def test_no_cpu_fallback_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('a GPU is present')
+    from dbb_b200.genomicSignatures import GenomicSignatures
+    with pytest.raises(_lib.DbbError):
+        GenomicSignatures(4, 1).seqSignature('ACGTACGT')
+    from dbb_b200 import _pairs
+    from dbb_b200.distributions import PairTables
+    with pytest.raises(_lib.DbbError):
+        _pairs.run_pairs_host(np.zeros((4, 136), np.float32), PairTables(np.array([1000, 2000, 3000, 4000])), k=2)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, 'dbb_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh')):
+                assert 'oracle' not in open(os.path.join(dirpath, f)).read(), f

@@ -1,0 +1,97 @@
+"""CPU: the oracle against the golden vectors that tests/golden/make_golden.py produced by executing the
+reference's own source files (this is what pins the oracle), plus literal-vs-vectorised self checks."""
+import hashlib
+
+import numpy as np
+from hypothesis import given, settings, strategies as st
+
+from oracle import dbb_oracle as O
+from tests import util
+
+
+def test_column_table_matches_reference_and_survey_hashes():
+    t = util.golden_json('ref_table.json')
+    assert t['kmerCols'] == O.KMER_COLS and t['numKmers'] == 136 == O.NUM_KMERS
+    assert t['kmerToCanonicalIndex'] == O.KMER_TO_INDEX
+    assert O.KMER_COLS == sorted(O.KMER_COLS)
+    assert sum(1 for k in O.KMER_COLS if O.rev_comp(k) == k) == 16
+    assert hashlib.sha256('\t'.join(O.KMER_COLS).encode()).hexdigest() == \
+        'e50eaf21f505fba2ce9262fc8b7e053c1e29a54a276be01e6227f2d1c3503422'
+    assert hashlib.sha256(bytes(O.code_lut256())).hexdigest() == \
+        '9a57f94a839828cfdd42650170aa4db6e761932f7724c8056ab4ea818d0bc72f'
+
+
+def test_signatures_match_reference_bit_for_bit():
+    kat = util.golden_json('ref_kat_seqs.json')
+    ref = util.golden_npz('ref_signatures.npz')['sigs']
+    assert len(kat) == ref.shape[0] >= 50
+    for s, g in zip(kat, ref):
+        assert np.array_equal(O.seq_signature_literal(s), g, equal_nan=True)
+        assert np.array_equal(O.seq_signature_np(s), g, equal_nan=True)
+
+
+def test_known_answers_by_hand():
+    c = O.seq_counts_literal('ACGT'); assert sum(c) == 1 and c[O.KMER_COLS.index('ACGT')] == 1
+    assert O.seq_counts_literal('AAAA') == O.seq_counts_literal('TTTT')
+    assert O.seq_counts_literal('AAAAA')[O.KMER_COLS.index('AAAA')] == 2
+    assert sum(O.seq_counts_literal('ACGNACGT')) == 1 and sum(O.seq_counts_literal('acgtACGT')) == 1
+    for s in ('', 'ACG', 'NNNN'):
+        assert sum(O.seq_counts_literal(s)) == 0 and np.isnan(O.seq_signature_literal(s)).all()
+    s = 'GATTACAGATTACACCGGTTAACC'
+    assert O.seq_counts_literal(s) == O.seq_counts_literal(O.rev_comp(s))
+
+
+@settings(max_examples=150, deadline=None)
+@given(st.text(alphabet='ACGTNacgtRYU', min_size=0, max_size=300))
+def test_literal_equals_vectorised(s):
+    assert O.seq_counts_literal(s) == O.seq_counts_np(s).tolist()
+    valid = sum(1 for i in range(len(s) - 3) if all(ch in 'ACGT' for ch in s[i:i + 4]))
+    assert sum(O.seq_counts_literal(s)) == valid
+
+
+def _golden_contigs():
+    nb = util.golden_npz('ref_neighbours.npz')
+    cs = [O.Contig('c%d' % i, int(nb['length'][i]), float(nb['GC'][i]), float(nb['coverage'][i]), nb['tetraSig'][i])
+          for i in range(len(nb['length']))]
+    return nb, cs
+
+
+def test_neighbour_rows_match_reference_loops():
+    from dbb_b200 import synthetic
+    from dbb_b200.data import load_td_dist
+    nb, cs = _golden_contigs()
+    td, gcd, cvd = load_td_dist(), synthetic.synthetic_gc_dist(), synthetic.synthetic_cov_dist(seed=7)
+    n = len(cs)
+    assert np.array_equal(np.array([[O.distance(a.tetraSig, b.tetraSig) for b in cs] for a in cs]), nb['distance'], equal_nan=True)
+    for tag, fixed, per in (('fixedNone_p80', None, 80), ('fixed10000_p80', 10000, 80), ('fixedNone_p99', None, 99)):
+        dT = O.Distributions(None, None, td, per, None, None)
+        dG = O.Distributions(gcd, per, None, None, None, None)
+        dC = O.Distributions(None, None, None, None, cvd, per)
+        tb = O.DistTables(gcd, per, td, per, cvd, per)
+        rows = list(range(n))
+        with np.errstate(invalid='ignore'):
+            assert np.array_equal(np.array([O.td_row_literal(c, cs, dT, fixed) for c in cs]), nb['td_' + tag])
+            assert np.array_equal(O.td_rows_np(nb['tetraSig'], nb['length'], rows, tb, fixed), nb['td_' + tag])
+        assert np.array_equal(np.array([O.gc_row_literal(c, cs, dG, fixed) for c in cs]), nb['gc_' + tag])
+        assert np.array_equal(np.array([O.cov_row_literal(c, cs, dC, fixed) for c in cs]), nb['cov_' + tag])
+        assert np.array_equal(O.gc_rows_np(nb['length'], nb['GC'], rows, tb, fixed), nb['gc_' + tag])
+        assert np.array_equal(O.cov_rows_np(nb['length'], nb['coverage'], rows, tb, fixed), nb['cov_' + tag])
+    # semantics the golden set was built to exercise
+    td80 = nb['td_fixedNone_p80']
+    assert (np.diag(td80)[np.arange(n) != 8] == 1).all()           # i == j is a neighbour ...
+    assert td80[8].sum() == 0 and td80[:, 8].sum() == 0             # ... except for a NaN signature
+    assert nb['length'][5] == nb['length'][6]                       # equal lengths: core = j in both orders
+
+
+def test_td_dist_values_from_survey():
+    from dbb_b200.data import load_td_dist
+    td = load_td_dist()
+    assert len(td) == 41 and len(td[500]) == 201
+    assert td[10000][80.0] == 0.1542 and td[10000][99.0] == 0.351339 and td[500][95.0] == 0.549141
+
+
+def test_tsv_format_is_py2_str():
+    assert O.format_sig_value(0.0073529411764705881) == '0.00735294117647'
+    assert O.format_sig_value(1.0) == '1.0' and O.format_sig_value(0.0) == '0.0'
+    assert O.format_sig_value(float('nan')) == 'nan' and O.format_sig_value(1e-05) == '1e-05'
+    assert O.tsv_header().startswith('Sequence Id\tAAAA\tAAAC') and O.tsv_header().count('\t') == 136
