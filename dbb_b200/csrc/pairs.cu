@@ -42,6 +42,7 @@ constexpr int COMPUTE_WARPS = 8;
 constexpr int THREADS = COMPUTE_WARPS * 32;       // 8 warps: register allocation is per 4 warps
 constexpr int PREFETCH = NSTAGE - 2;             // B chunks in flight ahead of the consumer
 constexpr int LIST_K = DBB_MAX_K;            // list slots per row
+constexpr int QCAP = 512;                    // queue entries per warp (>= 2 x the 256 pushes of one row pair)
 
 struct RowScalars {       // staged in shared memory per row tile
   int32_t len;
@@ -67,7 +68,13 @@ struct SmemLayout {
   alignas(128) float b[NSTAGE][TILE][KCH];
   float list_d[TILE][LIST_K];
   int32_t list_j[TILE][LIST_K];
+  float scratch[COMPUTE_WARPS][8][32];   // distances of one row pair, handed to the flood path
+  float qd[COMPUTE_WARPS][QCAP];         // per-warp queue of pairs that may be a neighbour or a top-k candidate
+  uint32_t qcode[COMPUTE_WARPS][QCAP];   //   (row within the warp's 16) << 7 | (column within the tile)
   RowScalars rows[TILE];
+  unsigned long long bp[TILE];           // neighbourhood base pairs per row
+  int32_t cnt[TILE];                     // neighbourhood size per row
+  float thr[TILE];                       // current k-th best distance per row (+inf until k found)
   alignas(8) uint64_t full[NSTAGE];
   uint64_t empty[NSTAGE];
   uint64_t a_full;
@@ -125,26 +132,168 @@ __device__ __forceinline__ float list_insert(SmemLayout& sm, int row, float d, i
   return __shfl_sync(0xffffffffu, ed, k - 1);
 }
 
-// rare path: all lanes whose bit is set in m hold a candidate (distance d) for row row2 + lane/16,
-// column colj + lane%16; returns the caller's updated k-th-best threshold
-__device__ __noinline__ float insert_candidates(SmemLayout& sm, uint32_t m, float d, float thr, int32_t colj,
-                                                int row2, int k, int lane) {
-  while (m) {
-    const int src = __ffs(m) - 1;
-    m &= m - 1;
-    const float cd = __shfl_sync(0xffffffffu, d, src);
-    const float nt = list_insert(sm, row2 + (src >> 4), cd, colj + (src & 15), k, lane);
-    if ((lane >> 4) == (src >> 4)) thr = nt;
+// Slow path of the epilogue (one call per row pair that may hold a neighbour or a top-k candidate):
+// evaluates the predicates of the 2 x 128 pairs whose distances sit in sm.scratch[warp], updates the
+// per-row counts / base pairs / masks / top-k lists.  Whole warp, lanes 0-15 -> row lr0, 16-31 -> lr0+1.
+template <int FLAGS>
+__device__ __noinline__ void process_row_pair(SmemLayout& sm, const Params& P, int warp, int lane, int lr0,
+                                              int64_t row_base, int64_t col_base) {
+  constexpr bool F_TD = (FLAGS & 1) != 0, F_GCCOV = (FLAGS & 2) != 0, F_MASK = (FLAGS & 4) != 0, F_TOPK = (FLAGS & 8) != 0;
+  const int ty = lane >> 4, tx = lane & 15;
+  const int lr = lr0 + ty;
+  const int64_t gi = row_base + lr;
+  const int64_t n = P.n;
+  const RowScalars rs = sm.rows[lr];
+  const bool has_gc = F_GCCOV && P.gc != nullptr, has_cov = F_GCCOV && P.cov != nullptr;
+  const bool want_cnt = P.count != nullptr || P.neighbour_bp != nullptr;
+  const int k = P.k;
+  #pragma unroll 1
+  for (int j = 0; j < 8; ++j) {
+    const float d = sm.scratch[warp][j][lane];
+    const int64_t cj = col_base + tx + 16 * j;
+    const bool col_ok = cj < n;
+    int32_t len_j = 0;
+    bool p_td = col_ok, p_gc = col_ok, p_cov = col_ok;
+    if (col_ok) {
+      len_j = __ldg(P.length + cj);
+      const bool i_core = rs.len > len_j;
+      if (F_TD) p_td = d < (i_core ? __ldg(P.td_bound + cj) : rs.tdb);
+      if (has_gc) {
+        const int m = i_core ? rs.gcm : __ldg(P.gc_mbin + cj), l = i_core ? __ldg(P.gc_lbin + cj) : rs.gcl;
+        const double lo = __ldg(P.gc_lo + m * P.gc_nl + l), hi = __ldg(P.gc_hi + m * P.gc_nl + l);
+        const double gj = __ldg(P.gc + cj);
+        const double diff = i_core ? (gj - rs.gc) : (rs.gc - gj);
+        p_gc = diff >= lo && diff <= hi;
+      }
+      if (has_cov) {
+        const double vj = __ldg(P.cov + cj);
+        const double cc = i_core ? rs.cov : vj, cu = i_core ? vj : rs.cov;
+        const int l = i_core ? __ldg(P.cov_lbin + cj) : rs.covl;
+        const double eff = cc > 0 ? cc : 0.1;
+        const double diff = (cu - eff) * 100.0 / eff;
+        p_cov = diff >= __ldg(P.cov_lo + l) && diff <= __ldg(P.cov_hi + l);
+      }
+    }
+    const bool all = p_td && p_gc && p_cov;
+    if (want_cnt) {
+      const uint32_t ball = __ballot_sync(0xffffffffu, all);
+      if (tx == 0) sm.cnt[lr] += __popc((ball >> (16 * ty)) & 0xffffu);
+      if (all) atomicAdd(&sm.bp[lr], (unsigned long long)len_j);
+    }
+    if (F_MASK) {
+      // one ballot = 16 consecutive columns of row lr0 (low half) and of row lr0+1 (high half)
+      const uint32_t bt = __ballot_sync(0xffffffffu, p_td);
+      const uint32_t bg = __ballot_sync(0xffffffffu, p_gc);
+      const uint32_t bc = __ballot_sync(0xffffffffu, p_cov);
+      const int64_t w = (col_base >> 5) + (j >> 1);
+      if (tx == 0 && gi < P.row1 && w < P.mask_words) {
+        const int sh = 16 * (j & 1);
+        const size_t o = (size_t)(gi - P.row0) * P.mask_words + w;
+        // the two 16-bit halves of a word are written by the same lane in consecutive j
+        if (P.td_mask && F_TD) { const uint32_t v = ((bt >> (16 * ty)) & 0xffffu) << sh; if (sh) P.td_mask[o] |= v; else P.td_mask[o] = v; }
+        if (P.gc_mask && has_gc) { const uint32_t v = ((bg >> (16 * ty)) & 0xffffu) << sh; if (sh) P.gc_mask[o] |= v; else P.gc_mask[o] = v; }
+        if (P.cov_mask && has_cov) { const uint32_t v = ((bc >> (16 * ty)) & 0xffffu) << sh; if (sh) P.cov_mask[o] |= v; else P.cov_mask[o] = v; }
+      }
+    }
+    if (F_TOPK) {
+      bool cand = col_ok && (cj != gi) && (d <= sm.thr[lr]);
+      if (P.topk_filter & 1) cand = cand && p_td;
+      if (P.topk_filter & 2) cand = cand && p_gc;
+      if (P.topk_filter & 4) cand = cand && p_cov;
+      uint32_t m = __ballot_sync(0xffffffffu, cand);
+      while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        const int crow = lr0 + (src >> 4);
+        const float cd = __shfl_sync(0xffffffffu, d, src);
+        if (cd <= sm.thr[crow]) {            // the list may have tightened since the ballot
+          const float nt = list_insert(sm, crow, cd, (int32_t)(col_base + (src & 15) + 16 * j), k, lane);
+          if (lane == 0) sm.thr[crow] = nt;
+        }
+        __syncwarp();
+      }
+    }
   }
-  return thr;
+  __syncwarp();
+}
+
+// Steady-state slow path: the warp's queue holds (distance, row, column) of the few pairs of this column
+// tile that passed the conservative in-register test.  Lane-parallel predicates and counts, then the
+// (rare) top-k candidates are inserted one at a time, warp-cooperatively.
+template <int FLAGS>
+__device__ __noinline__ void drain_queue(SmemLayout& sm, const Params& P, int warp, int lane, int qn,
+                                         int64_t row_base, int64_t col_base) {
+  constexpr bool F_TD = (FLAGS & 1) != 0, F_GCCOV = (FLAGS & 2) != 0, F_TOPK = (FLAGS & 8) != 0;
+  const int64_t n = P.n;
+  const bool has_gc = F_GCCOV && P.gc != nullptr, has_cov = F_GCCOV && P.cov != nullptr;
+  const bool want_cnt = P.count != nullptr || P.neighbour_bp != nullptr;
+  const int k = P.k;
+  #pragma unroll 1
+  for (int base = 0; base < qn; base += 32) {
+    const int e = base + lane;
+    const bool valid = e < qn;
+    const float d = valid ? sm.qd[warp][e] : INFINITY;
+    const uint32_t code = valid ? sm.qcode[warp][e] : 0u;
+    const int lr = warp * 16 + (int)(code >> 7);
+    const int64_t cj = col_base + (code & 127u);
+    const int64_t gi = row_base + lr;
+    const bool col_ok = valid && cj < n;
+    int32_t len_j = 0;
+    bool p_td = col_ok, p_gc = col_ok, p_cov = col_ok;
+    if (col_ok) {
+      const RowScalars rs = sm.rows[lr];
+      len_j = __ldg(P.length + cj);
+      const bool i_core = rs.len > len_j;
+      if (F_TD) p_td = d < (i_core ? __ldg(P.td_bound + cj) : rs.tdb);
+      if (has_gc) {
+        const int m = i_core ? rs.gcm : __ldg(P.gc_mbin + cj), l = i_core ? __ldg(P.gc_lbin + cj) : rs.gcl;
+        const double lo = __ldg(P.gc_lo + m * P.gc_nl + l), hi = __ldg(P.gc_hi + m * P.gc_nl + l);
+        const double gj = __ldg(P.gc + cj);
+        const double diff = i_core ? (gj - rs.gc) : (rs.gc - gj);
+        p_gc = diff >= lo && diff <= hi;
+      }
+      if (has_cov) {
+        const double vj = __ldg(P.cov + cj);
+        const double cc = i_core ? rs.cov : vj, cu = i_core ? vj : rs.cov;
+        const int l = i_core ? __ldg(P.cov_lbin + cj) : rs.covl;
+        const double eff = cc > 0 ? cc : 0.1;
+        const double diff = (cu - eff) * 100.0 / eff;
+        p_cov = diff >= __ldg(P.cov_lo + l) && diff <= __ldg(P.cov_hi + l);
+      }
+    }
+    if (want_cnt && p_td && p_gc && p_cov) {
+      atomicAdd(&sm.cnt[lr], 1);
+      atomicAdd(&sm.bp[lr], (unsigned long long)len_j);
+    }
+    if (F_TOPK) {
+      bool cand = col_ok && (cj != gi) && (d <= sm.thr[lr]);
+      if (P.topk_filter & 1) cand = cand && p_td;
+      if (P.topk_filter & 2) cand = cand && p_gc;
+      if (P.topk_filter & 4) cand = cand && p_cov;
+      uint32_t m = __ballot_sync(0xffffffffu, cand);
+      while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        const int crow = __shfl_sync(0xffffffffu, lr, src);
+        const float cd = __shfl_sync(0xffffffffu, d, src);
+        const int32_t cc = (int32_t)__shfl_sync(0xffffffffu, (int)cj, src);
+        if (cd <= sm.thr[crow]) {
+          const float nt = list_insert(sm, crow, cd, cc, k, lane);
+          if (lane == 0) sm.thr[crow] = nt;
+        }
+        __syncwarp();
+      }
+    }
+  }
+  __syncwarp();
 }
 
 // FLAGS: bit0 TD predicate, bit1 GC and/or coverage predicates, bit2 masks, bit3 top-k
 template <int FLAGS>
-__global__ void __launch_bounds__(THREADS, 1) pairs_kernel(const __grid_constant__ CUtensorMap tmap, const Params P) {
+__global__ void __launch_bounds__(THREADS, 1) pairs_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Params P) {
   constexpr bool F_TD = (FLAGS & 1) != 0, F_GCCOV = (FLAGS & 2) != 0, F_MASK = (FLAGS & 4) != 0, F_TOPK = (FLAGS & 8) != 0;
-  extern __shared__ uint8_t smem_raw[];
-  SmemLayout& sm = *reinterpret_cast<SmemLayout*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  SmemLayout& sm = *reinterpret_cast<SmemLayout*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t n = P.n;
   const int64_t n_rows = P.row1 - P.row0;
@@ -159,11 +308,11 @@ __global__ void __launch_bounds__(THREADS, 1) pairs_kernel(const __grid_constant
   }
   __syncthreads();
 
-  // ================= compute warps =================
   const int ty = lane >> 4, tx = lane & 15;
-  const int k = P.k;
-  const bool has_td = F_TD, has_gc = F_GCCOV && P.gc != nullptr, has_cov = F_GCCOV && P.cov != nullptr;
+  const bool has_gc = F_GCCOV && P.gc != nullptr, has_cov = F_GCCOV && P.cov != nullptr;
   const bool want_cnt = P.count != nullptr || P.neighbour_bp != nullptr;
+  // without a TD bound the distance cannot veto a neighbour: every pair takes the full path
+  const bool always_slow = F_MASK || (want_cnt && !F_TD);
   uint32_t q = 0, rt_iter = 0;
   // B chunks of this CTA form one sequence over all its row sweeps: chunk pq is K-chunk pq%5 of
   // column tile (pq/5) % n_ct; it lands in ring stage pq % NSTAGE
@@ -178,31 +327,28 @@ __global__ void __launch_bounds__(THREADS, 1) pairs_kernel(const __grid_constant
 
   for (int rt = blockIdx.x; rt < n_rt; rt += gridDim.x, ++rt_iter) {
     const int64_t row_base = P.row0 + (int64_t)rt * TILE;
-    // stage row scalars and reset the top-k lists of this warp's 16 rows
-    for (int r = lane; r < 16; r += 32) {
-      const int lr = warp * 16 + r;
+    // stage row scalars and reset the per-row state of this warp's 16 rows
+    if (lane < 16) {
+      const int lr = warp * 16 + lane;
       const int64_t gr = row_base + lr;
       RowScalars rs;
       rs.len = 0; rs.tdb = 0.f; rs.gcm = 0; rs.gcl = 0; rs.covl = 0; rs.pad = 0; rs.gc = 0.0; rs.cov = 0.0;
       if (gr < n) {
         rs.len = P.length[gr];
-        if (has_td) rs.tdb = P.td_bound[gr];
+        if (F_TD) rs.tdb = P.td_bound[gr];
         if (has_gc) { rs.gc = P.gc[gr]; rs.gcm = P.gc_mbin[gr]; rs.gcl = P.gc_lbin[gr]; }
         if (has_cov) { rs.cov = P.cov[gr]; rs.covl = P.cov_lbin[gr]; }
       }
       sm.rows[lr] = rs;
+      sm.cnt[lr] = 0;
+      sm.bp[lr] = 0ull;
+      sm.thr[lr] = F_TOPK ? INFINITY : -INFINITY;
     }
     for (int r = 0; r < 16; ++r) {
       sm.list_d[warp * 16 + r][lane] = INFINITY;
       sm.list_j[warp * 16 + r][lane] = INT_MAX;
     }
     __syncwarp();
-
-    float thr[8];
-    int32_t cnt[8];
-    long long bp[8];
-    #pragma unroll
-    for (int i = 0; i < 8; ++i) { thr[i] = INFINITY; cnt[i] = 0; bp[i] = 0; }
 
     // thread 0 doubles as the TMA producer: A tile of this sweep + the first PREFETCH B chunks
     if (tid == 0) {
@@ -226,15 +372,17 @@ __global__ void __launch_bounds__(THREADS, 1) pairs_kernel(const __grid_constant
         if (tid == 0 && q + PREFETCH < total_chunks) issue_b(q + PREFETCH);
         mbar_wait(&sm.full[st], (q / NSTAGE) & 1);
         const float* ap = &sm.a[kc][warp * 16 + ty][0];
-        const float* bp_ = &sm.b[st][tx][0];
-        #pragma unroll
+        const float* bq = &sm.b[st][tx][0];
+        // NOT unrolled: one k4 step is ~280 instructions (4.4 KB); unrolling all 7 made the loop 31 KB and
+        // instruction-fetch stalls ("no_instruction") cost ~25 % (profiles/r01_pairs_notes.md)
+        #pragma unroll 1
         for (int k4 = 0; k4 < KCH / 4; ++k4) {
           float4 av[8];
           #pragma unroll
           for (int i = 0; i < 8; ++i) av[i] = *reinterpret_cast<const float4*>(ap + (2 * i) * KCH + k4 * 4);
           #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float4 bv = *reinterpret_cast<const float4*>(bp_ + (16 * j) * KCH + k4 * 4);
+            const float4 bv = *reinterpret_cast<const float4*>(bq + (16 * j) * KCH + k4 * 4);
             #pragma unroll
             for (int i = 0; i < 8; ++i) {
               acc[i][j] = absdiff_acc(acc[i][j], make_float2(av[i].x, av[i].y), make_float2(bv.x, bv.y));
@@ -248,70 +396,53 @@ __global__ void __launch_bounds__(THREADS, 1) pairs_kernel(const __grid_constant
 
       // ---------------- epilogue of this column tile ----------------
       const int64_t col_base = (int64_t)ct * TILE;
-      #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int64_t cj = col_base + tx + 16 * j;
-        const bool col_ok = cj < n;
-        int32_t len_j = 0; float tdb_j = 0.f;
-        double gc_j = 0.0, cov_j = 0.0; int32_t gcm_j = 0, gcl_j = 0, covl_j = 0;
-        if (col_ok) {
-          len_j = __ldg(P.length + cj);
-          if (has_td) tdb_j = __ldg(P.td_bound + cj);
-          if (has_gc) { gc_j = __ldg(P.gc + cj); gcm_j = __ldg(P.gc_mbin + cj); gcl_j = __ldg(P.gc_lbin + cj); }
-          if (has_cov) { cov_j = __ldg(P.cov + cj); covl_j = __ldg(P.cov_lbin + cj); }
+      if (always_slow || (F_TOPK && ct == 0)) {
+        // flood tiles (every pair matters: masks, counts without a TD bound, or empty top-k lists)
+        #pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          #pragma unroll
+          for (int j = 0; j < 8; ++j) sm.scratch[warp][j][lane] = acc[i][j].x + acc[i][j].y;
+          __syncwarp();
+          process_row_pair<FLAGS>(sm, P, warp, lane, warp * 16 + 2 * i, row_base, col_base);
         }
+      } else {
+        // steady state: a pair is queued only if it can be a TD neighbour (d below the larger of the two
+        // bounds -- the exact rule is re-applied in the drain) or can enter the row's top-k (d <= k-th best)
+        float tdb_c[8];
+        #pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int64_t cj = col_base + tx + 16 * j;
+          tdb_c[j] = (F_TD && cj < n) ? __ldg(P.td_bound + cj) : -INFINITY;
+        }
+        int qn = 0;
+        const uint32_t lt_mask = (1u << lane) - 1u;
         #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int lr = warp * 16 + 2 * i + ty;
-          const int64_t gi = row_base + lr;
-          const RowScalars& rs = sm.rows[lr];
-          const float d = acc[i][j].x + acc[i][j].y;
-          const bool i_core = rs.len > len_j;
-          bool p_td = true, p_gc = true, p_cov = true;
-          if (has_td) p_td = d < (i_core ? tdb_j : rs.tdb);
-          if (has_gc) {
-            const int m = i_core ? rs.gcm : gcm_j, l = i_core ? gcl_j : rs.gcl;
-            const double lo = __ldg(P.gc_lo + m * P.gc_nl + l), hi = __ldg(P.gc_hi + m * P.gc_nl + l);
-            const double diff = i_core ? (gc_j - rs.gc) : (rs.gc - gc_j);
-            p_gc = diff >= lo && diff <= hi;
-          }
-          if (has_cov) {
-            const double cc = i_core ? rs.cov : cov_j, cu = i_core ? cov_j : rs.cov;
-            const int l = i_core ? covl_j : rs.covl;
-            const double eff = cc > 0 ? cc : 0.1;
-            const double diff = (cu - eff) * 100.0 / eff;
-            p_cov = diff >= __ldg(P.cov_lo + l) && diff <= __ldg(P.cov_hi + l);
-          }
-          p_td = p_td && col_ok; p_gc = p_gc && col_ok; p_cov = p_cov && col_ok;
-          const bool all = p_td && p_gc && p_cov;
-          if (want_cnt && all) { cnt[i] += 1; bp[i] += len_j; }
-
-          if (F_MASK) {
-            // one ballot = 16 columns of row (ty=0) in the low half, of row (ty=1) in the high half
-            const uint32_t bt = __ballot_sync(0xffffffffu, p_td);
-            const uint32_t bg = __ballot_sync(0xffffffffu, p_gc);
-            const uint32_t bc = __ballot_sync(0xffffffffu, p_cov);
-            if (tx == 0 && gi < P.row1) {
-              const int64_t w = (col_base >> 5) + (j >> 1);
-              if (w < P.mask_words) {
-                const int sh = 16 * (j & 1);
-                const size_t o = (size_t)(gi - P.row0) * P.mask_words + w;
-                // the two 16-bit halves of a word are written by the same lane in consecutive j
-                if (P.td_mask) { uint32_t v = ((bt >> (16 * ty)) & 0xffffu) << sh; if (sh) P.td_mask[o] |= v; else P.td_mask[o] = v; }
-                if (P.gc_mask && has_gc) { uint32_t v = ((bg >> (16 * ty)) & 0xffffu) << sh; if (sh) P.gc_mask[o] |= v; else P.gc_mask[o] = v; }
-                if (P.cov_mask && has_cov) { uint32_t v = ((bc >> (16 * ty)) & 0xffffu) << sh; if (sh) P.cov_mask[o] |= v; else P.cov_mask[o] = v; }
+          const float u = fmaxf(F_TD ? sm.rows[lr].tdb : -INFINITY, sm.thr[lr]);
+          #pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float d = acc[i][j].x + acc[i][j].y;
+            const bool hot = d <= fmaxf(u, tdb_c[j]);
+            const uint32_t m = __ballot_sync(0xffffffffu, hot);
+            if (m) {
+              if (hot) {
+                const int slot = qn + __popc(m & lt_mask);
+                sm.qd[warp][slot] = d;
+                sm.qcode[warp][slot] = (uint32_t)((2 * i + ty) << 7) | (uint32_t)(tx + 16 * j);
               }
+              qn += __popc(m);
             }
           }
-
-          if (F_TOPK) {
-            bool cand = col_ok && (cj != gi) && (d <= thr[i]);
-            if (P.topk_filter & 1) cand = cand && p_td;
-            if (P.topk_filter & 2) cand = cand && p_gc;
-            if (P.topk_filter & 4) cand = cand && p_cov;
-            const uint32_t m = __ballot_sync(0xffffffffu, cand);
-            if (m) thr[i] = insert_candidates(sm, m, d, thr[i], (int32_t)(col_base + 16 * j), warp * 16 + 2 * i, k, lane);
+          if (qn > QCAP - 256) {
+            __syncwarp();
+            drain_queue<FLAGS>(sm, P, warp, lane, qn, row_base, col_base);
+            qn = 0;
           }
+        }
+        if (qn) {
+          __syncwarp();
+          drain_queue<FLAGS>(sm, P, warp, lane, qn, row_base, col_base);
         }
       }
     }  // column tiles
@@ -321,22 +452,16 @@ __global__ void __launch_bounds__(THREADS, 1) pairs_kernel(const __grid_constant
     if (lane == 0) mbar_arrive(&sm.a_empty);
 
     // ---------------- per-row outputs ----------------
-    #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      int32_t c = cnt[i];
-      long long b = bp[i];
-      #pragma unroll
-      for (int dlt = 8; dlt > 0; dlt >>= 1) {
-        c += __shfl_xor_sync(0xffffffffu, c, dlt);
-        b += __shfl_xor_sync(0xffffffffu, b, dlt);
-      }
-      const int64_t gi = row_base + warp * 16 + 2 * i + ty;
-      if (tx == 0 && gi < P.row1) {
-        if (P.count) P.count[gi - P.row0] = c;
-        if (P.neighbour_bp) P.neighbour_bp[gi - P.row0] = b;
+    if (lane < 16) {
+      const int lr = warp * 16 + lane;
+      const int64_t gi = row_base + lr;
+      if (gi < P.row1) {
+        if (P.count) P.count[gi - P.row0] = sm.cnt[lr];
+        if (P.neighbour_bp) P.neighbour_bp[gi - P.row0] = (int64_t)sm.bp[lr];
       }
     }
     if (F_TOPK) {
+      const int k = P.k;
       for (int r = 0; r < 16; ++r) {
         const int lr = warp * 16 + r;
         const int64_t gi = row_base + lr;
