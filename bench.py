@@ -296,7 +296,7 @@ def run_ours(args):
     ms_knn = max_over_ranks(sum(e[2].elapsed_time(e[3]) for e in ev) / args.steps)
     ms_step = total_ms / args.steps
     pairs_total = float(n_total) * float(n_total)
-    launches_per_step = plan.launches + 1
+    launches_per_step = plan.launches + int(_lib.lib().dbb_pairs_launches(n_total, r1 - r0))
 
     # ---------------- end-to-end through the host-buffer C ABI (H2D + D2H inside the timed region) --------
     h_ascii = torch.empty(d_ascii.shape, dtype=torch.uint8, pin_memory=True)

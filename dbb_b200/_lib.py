@@ -52,6 +52,7 @@ SIGNATURES = {
     'dbb_tetra_signatures_host': (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
     'dbb_pairs_dev': (ctypes.c_int, [ctypes.POINTER(PairsInput), c_i64, c_i64, ctypes.POINTER(PairsOutput), c_vp]),
     'dbb_pairs_scratch_bytes': (c_i64, [c_i64, c_i64, c_i32]),
+    'dbb_pairs_launches': (ctypes.c_int, [c_i64, c_i64]),
     'dbb_pairs_host': (ctypes.c_int, [ctypes.POINTER(PairsInput), c_i64, c_i64, ctypes.POINTER(PairsOutput)]),
     'dbb_pad_signatures_dev': (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp]),
     'dbb_synth_ascii_dev': (ctypes.c_int, [ctypes.c_uint64, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp,

@@ -30,6 +30,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <climits>
+#include <cstdlib>
 
 namespace {
 
@@ -61,6 +62,11 @@ struct Params {
   int32_t k, topk_filter;
   int32_t* knn_idx; float* knn_dist; int32_t* count; int64_t* neighbour_bp;
   uint32_t* td_mask; uint32_t* gc_mask; uint32_t* cov_mask; int64_t mask_words;
+  // work items: row tiles [0, n_full_rt) are swept over all columns by one CTA; each remaining row tile is
+  // split into n_seg column segments (separate items) whose partial results are merged afterwards
+  int32_t n_full_rt, n_seg, n_items;
+  uint32_t* item_counter;
+  int32_t* part_idx; float* part_dist; int32_t* part_cnt; int64_t* part_bp;
 };
 
 struct SmemLayout {
@@ -72,13 +78,13 @@ struct SmemLayout {
   float qd[COMPUTE_WARPS][QCAP];         // per-warp queue of pairs that may be a neighbour or a top-k candidate
   uint32_t qcode[COMPUTE_WARPS][QCAP];   //   (row within the warp's 16) << 7 | (column within the tile)
   RowScalars rows[TILE];
-  unsigned long long bp[TILE];           // neighbourhood base pairs per row
+  uint32_t bp_lo[TILE], bp_hi[TILE];     // neighbourhood base pairs per row (64-bit as two native 32-bit atomics)
   int32_t cnt[TILE];                     // neighbourhood size per row
   float thr[TILE];                       // current k-th best distance per row (+inf until k found)
   alignas(8) uint64_t full[NSTAGE];
   uint64_t empty[NSTAGE];
   uint64_t a_full;
-  uint64_t a_empty;
+  int32_t item;
 };
 
 // ---- mbarrier / TMA primitives ------------------------------------------------------------------
@@ -112,6 +118,11 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
 __device__ __forceinline__ float2 absdiff_acc(float2 acc, float2 a, float2 b) {
   float2 d = __fadd2_rn(a, make_float2(-b.x, -b.y));
   return __fadd2_rn(acc, make_float2(fabsf(d.x), fabsf(d.y)));
+}
+
+__device__ __forceinline__ void add_bp(SmemLayout& sm, int lr, uint32_t v) {
+  const uint32_t old = atomicAdd(&sm.bp_lo[lr], v);
+  if (old + v < old) atomicAdd(&sm.bp_hi[lr], 1u);
 }
 
 // warp-cooperative insertion of (d, c) into the sorted list of `row`; returns the new k-th best
@@ -178,7 +189,7 @@ __device__ __noinline__ void process_row_pair(SmemLayout& sm, const Params& P, i
     if (want_cnt) {
       const uint32_t ball = __ballot_sync(0xffffffffu, all);
       if (tx == 0) sm.cnt[lr] += __popc((ball >> (16 * ty)) & 0xffffu);
-      if (all) atomicAdd(&sm.bp[lr], (unsigned long long)len_j);
+      if (all) add_bp(sm, lr, (uint32_t)len_j);
     }
     if (F_MASK) {
       // one ballot = 16 consecutive columns of row lr0 (low half) and of row lr0+1 (high half)
@@ -263,7 +274,7 @@ __device__ __noinline__ void drain_queue(SmemLayout& sm, const Params& P, int wa
     }
     if (want_cnt && p_td && p_gc && p_cov) {
       atomicAdd(&sm.cnt[lr], 1);
-      atomicAdd(&sm.bp[lr], (unsigned long long)len_j);
+      add_bp(sm, lr, (uint32_t)len_j);
     }
     if (F_TOPK) {
       bool cand = col_ok && (cj != gi) && (d <= sm.thr[lr]);
@@ -303,30 +314,52 @@ __global__ void __launch_bounds__(THREADS, 1) pairs_kernel(const __grid_constant
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], COMPUTE_WARPS); }
     mbar_init(&sm.a_full, 1);
-    mbar_init(&sm.a_empty, COMPUTE_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __syncthreads();
 
   const int ty = lane >> 4, tx = lane & 15;
   const bool has_gc = F_GCCOV && P.gc != nullptr, has_cov = F_GCCOV && P.cov != nullptr;
   const bool want_cnt = P.count != nullptr || P.neighbour_bp != nullptr;
   // without a TD bound the distance cannot veto a neighbour: every pair takes the full path
   const bool always_slow = F_MASK || (want_cnt && !F_TD);
-  uint32_t q = 0, rt_iter = 0;
-  // B chunks of this CTA form one sequence over all its row sweeps: chunk pq is K-chunk pq%5 of
-  // column tile (pq/5) % n_ct; it lands in ring stage pq % NSTAGE
-  const uint32_t my_rt = (n_rt > (int)blockIdx.x) ? (uint32_t)((n_rt - 1 - (int)blockIdx.x) / (int)gridDim.x + 1) : 0u;
-  const uint32_t total_chunks = my_rt * (uint32_t)n_ct * NKC;
-  auto issue_b = [&](uint32_t pq) {
-    const uint32_t st = pq % NSTAGE;
-    if (pq >= NSTAGE) mbar_wait(&sm.empty[st], ((pq / NSTAGE) - 1) & 1);
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  uint32_t q = 0;          // B chunks consumed so far by this CTA (ring position / mbarrier phase)
+  uint32_t items_done = 0;
+
+  // B chunk `l` of the current item (K-chunk l%5 of column tile ct0 + l/5) goes to ring stage (qbase+l)%NSTAGE
+  auto issue_b = [&](uint32_t qg, int ctile, int kc) {
+    const uint32_t st = qg % NSTAGE;
+    if (qg >= NSTAGE) mbar_wait(&sm.empty[st], ((qg / NSTAGE) - 1) & 1);
     mbar_arrive_expect_tx(&sm.full[st], CHUNK_BYTES);
-    tma_load_2d(&sm.b[st][0][0], &tmap, (int32_t)((pq % NKC) * KCH), (int32_t)(((pq / NKC) % (uint32_t)n_ct) * TILE), &sm.full[st]);
+    tma_load_2d(&sm.b[st][0][0], &tmap, kc * KCH, ctile * TILE, &sm.full[st]);
   };
 
-  for (int rt = blockIdx.x; rt < n_rt; rt += gridDim.x, ++rt_iter) {
+  while (true) {
+    __syncthreads();                       // everyone is done with the previous item's A tile and lists
+    if (tid == 0) sm.item = (int32_t)atomicAdd(P.item_counter, 1u);
+    __syncthreads();
+    const int item = sm.item;
+    if (item >= P.n_items) break;
+    int rt, seg = -1, ct0 = 0, ct1 = n_ct;
+    if (item < P.n_full_rt) {
+      rt = item;
+    } else {
+      const int t = item - P.n_full_rt;
+      rt = P.n_full_rt + t / P.n_seg;
+      seg = t % P.n_seg;
+      ct0 = (int)(((int64_t)n_ct * seg) / P.n_seg);
+      ct1 = (int)(((int64_t)n_ct * (seg + 1)) / P.n_seg);
+    }
     const int64_t row_base = P.row0 + (int64_t)rt * TILE;
+    const uint32_t item_chunks = (uint32_t)(ct1 - ct0) * NKC;
+    const uint32_t qbase = q;
+
+    // thread 0 doubles as the TMA producer: A tile of this item + its first PREFETCH B chunks
+    if (tid == 0) {
+      mbar_arrive_expect_tx(&sm.a_full, NKC * CHUNK_BYTES);
+      for (int kc = 0; kc < NKC; ++kc) tma_load_2d(&sm.a[kc][0][0], &tmap, kc * KCH, (int32_t)row_base, &sm.a_full);
+      for (uint32_t l = 0; l < (uint32_t)PREFETCH && l < item_chunks; ++l) issue_b(qbase + l, ct0 + (int)(l / NKC), (int)(l % NKC));
+    }
     // stage row scalars and reset the per-row state of this warp's 16 rows
     if (lane < 16) {
       const int lr = warp * 16 + lane;
@@ -341,7 +374,7 @@ __global__ void __launch_bounds__(THREADS, 1) pairs_kernel(const __grid_constant
       }
       sm.rows[lr] = rs;
       sm.cnt[lr] = 0;
-      sm.bp[lr] = 0ull;
+      sm.bp_lo[lr] = 0u; sm.bp_hi[lr] = 0u;
       sm.thr[lr] = F_TOPK ? INFINITY : -INFINITY;
     }
     for (int r = 0; r < 16; ++r) {
@@ -349,27 +382,23 @@ __global__ void __launch_bounds__(THREADS, 1) pairs_kernel(const __grid_constant
       sm.list_j[warp * 16 + r][lane] = INT_MAX;
     }
     __syncwarp();
+    mbar_wait(&sm.a_full, items_done & 1);
 
-    // thread 0 doubles as the TMA producer: A tile of this sweep + the first PREFETCH B chunks
-    if (tid == 0) {
-      if (rt_iter > 0) mbar_wait(&sm.a_empty, (rt_iter - 1) & 1);
-      mbar_arrive_expect_tx(&sm.a_full, NKC * CHUNK_BYTES);
-      for (int kc = 0; kc < NKC; ++kc) tma_load_2d(&sm.a[kc][0][0], &tmap, kc * KCH, (int32_t)row_base, &sm.a_full);
-      if (rt_iter == 0)
-        for (uint32_t pq = 0; pq < (uint32_t)PREFETCH && pq < total_chunks; ++pq) issue_b(pq);
-    }
-    mbar_wait(&sm.a_full, rt_iter & 1);
-
-    for (int ct = 0; ct < n_ct; ++ct) {
+    uint32_t l = 0;                        // chunk index within the item
+    for (int ct = ct0; ct < ct1; ++ct) {
       float2 acc[8][8];
       #pragma unroll
       for (int i = 0; i < 8; ++i)
         #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = make_float2(0.f, 0.f);
 
-      for (int kc = 0; kc < NKC; ++kc, ++q) {
+      #pragma unroll 1
+      for (int kc = 0; kc < NKC; ++kc, ++q, ++l) {
         const uint32_t st = q % NSTAGE;
-        if (tid == 0 && q + PREFETCH < total_chunks) issue_b(q + PREFETCH);
+        if (tid == 0 && l + PREFETCH < item_chunks) {
+          const uint32_t ln = l + PREFETCH;
+          issue_b(qbase + ln, ct0 + (int)(ln / NKC), (int)(ln % NKC));
+        }
         mbar_wait(&sm.full[st], (q / NSTAGE) & 1);
         const float* ap = &sm.a[kc][warp * 16 + ty][0];
         const float* bq = &sm.b[st][tx][0];
@@ -396,7 +425,7 @@ __global__ void __launch_bounds__(THREADS, 1) pairs_kernel(const __grid_constant
 
       // ---------------- epilogue of this column tile ----------------
       const int64_t col_base = (int64_t)ct * TILE;
-      if (always_slow || (F_TOPK && ct == 0)) {
+      if (always_slow || (F_TOPK && ct == ct0)) {
         // flood tiles (every pair matters: masks, counts without a TD bound, or empty top-k lists)
         #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -415,23 +444,35 @@ __global__ void __launch_bounds__(THREADS, 1) pairs_kernel(const __grid_constant
           tdb_c[j] = (F_TD && cj < n) ? __ldg(P.td_bound + cj) : -INFINITY;
         }
         int qn = 0;
-        const uint32_t lt_mask = (1u << lane) - 1u;
         #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int lr = warp * 16 + 2 * i + ty;
           const float u = fmaxf(F_TD ? sm.rows[lr].tdb : -INFINITY, sm.thr[lr]);
+          uint32_t bits = 0;
           #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float d = acc[i][j].x + acc[i][j].y;
-            const bool hot = d <= fmaxf(u, tdb_c[j]);
-            const uint32_t m = __ballot_sync(0xffffffffu, hot);
-            if (m) {
-              if (hot) {
-                const int slot = qn + __popc(m & lt_mask);
-                sm.qd[warp][slot] = d;
+            acc[i][j].x = d;
+            bits |= (d <= fmaxf(u, tdb_c[j])) ? (1u << j) : 0u;
+          }
+          if (__any_sync(0xffffffffu, bits != 0u)) {
+            // exclusive prefix sum of the per-lane hit counts -> queue slots
+            const int c = __popc(bits);
+            int incl = c;
+            #pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+              const int t = __shfl_up_sync(0xffffffffu, incl, o);
+              if (lane >= o) incl += t;
+            }
+            int slot = qn + incl - c;
+            qn += __shfl_sync(0xffffffffu, incl, 31);
+            #pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (bits & (1u << j)) {
+                sm.qd[warp][slot] = acc[i][j].x;
                 sm.qcode[warp][slot] = (uint32_t)((2 * i + ty) << 7) | (uint32_t)(tx + 16 * j);
+                ++slot;
               }
-              qn += __popc(m);
             }
           }
           if (qn > QCAP - 256) {
@@ -447,33 +488,85 @@ __global__ void __launch_bounds__(THREADS, 1) pairs_kernel(const __grid_constant
       }
     }  // column tiles
 
-    // this warp is done with the A tile of this row sweep
+    // ---------------- per-row outputs (final for whole sweeps, partial for column segments) -----------
     __syncwarp();
-    if (lane == 0) mbar_arrive(&sm.a_empty);
-
-    // ---------------- per-row outputs ----------------
+    const int k = P.k;
     if (lane < 16) {
       const int lr = warp * 16 + lane;
       const int64_t gi = row_base + lr;
       if (gi < P.row1) {
-        if (P.count) P.count[gi - P.row0] = sm.cnt[lr];
-        if (P.neighbour_bp) P.neighbour_bp[gi - P.row0] = (int64_t)sm.bp[lr];
+        const int64_t bp = (int64_t)(((unsigned long long)sm.bp_hi[lr] << 32) | sm.bp_lo[lr]);
+        if (seg < 0) {
+          if (P.count) P.count[gi - P.row0] = sm.cnt[lr];
+          if (P.neighbour_bp) P.neighbour_bp[gi - P.row0] = bp;
+        } else {
+          const int64_t o = ((int64_t)(rt - P.n_full_rt) * TILE + lr) * P.n_seg + seg;
+          P.part_cnt[o] = sm.cnt[lr];
+          P.part_bp[o] = bp;
+        }
       }
     }
     if (F_TOPK) {
-      const int k = P.k;
       for (int r = 0; r < 16; ++r) {
         const int lr = warp * 16 + r;
         const int64_t gi = row_base + lr;
         if (gi < P.row1 && lane < k) {
           const int32_t ej = sm.list_j[lr][lane];
-          if (P.knn_idx) P.knn_idx[(gi - P.row0) * k + lane] = (ej == INT_MAX) ? -1 : ej;
-          if (P.knn_dist) P.knn_dist[(gi - P.row0) * k + lane] = sm.list_d[lr][lane];
+          const float ed = sm.list_d[lr][lane];
+          if (seg < 0) {
+            if (P.knn_idx) P.knn_idx[(gi - P.row0) * k + lane] = (ej == INT_MAX) ? -1 : ej;
+            if (P.knn_dist) P.knn_dist[(gi - P.row0) * k + lane] = ed;
+          } else {
+            const int64_t o = (((int64_t)(rt - P.n_full_rt) * TILE + lr) * P.n_seg + seg) * k + lane;
+            P.part_idx[o] = ej;
+            P.part_dist[o] = ed;
+          }
         }
       }
     }
-    __syncwarp();
-  }  // row tiles
+    ++items_done;
+  }  // items
+}
+
+// Merge of the partial results of split row tiles: one warp per row, lane l holds entry l of the sorted
+// list; the (distance, index) order is total, so the merged list is the same as an unsplit sweep's.
+__global__ void __launch_bounds__(128) merge_kernel(const Params P, int64_t first_row, int64_t n_split_rows) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (r >= n_split_rows) return;
+  const int64_t gi = first_row + r;             // row index relative to row0
+  const int k = P.k;
+  int32_t cnt = 0;
+  int64_t bp = 0;
+  for (int sgi = 0; sgi < P.n_seg; ++sgi) { cnt += P.part_cnt[r * P.n_seg + sgi]; bp += P.part_bp[r * P.n_seg + sgi]; }
+  if (lane == 0) {
+    if (P.count) P.count[gi] = cnt;
+    if (P.neighbour_bp) P.neighbour_bp[gi] = bp;
+  }
+  if (k > 0) {
+    float ed = INFINITY;
+    int32_t ej = INT_MAX;
+    for (int sgi = 0; sgi < P.n_seg; ++sgi) {
+      for (int e = 0; e < k; ++e) {
+        const int64_t o = (r * P.n_seg + sgi) * k + e;
+        const float d = P.part_dist[o];
+        const int32_t c = P.part_idx[o];
+        if (c == INT_MAX) break;              // lists are sorted: the rest is padding
+        const bool before = (ed < d) || (ed == d && ej < c);
+        const int pos = __popc(__ballot_sync(0xffffffffu, before));
+        const float pd = __shfl_up_sync(0xffffffffu, ed, 1);
+        const int32_t pj = __shfl_up_sync(0xffffffffu, ej, 1);
+        if (pos < k) {
+          if (lane == pos) { ed = d; ej = c; }
+          else if (lane > pos) { ed = pd; ej = pj; }
+        }
+      }
+    }
+    if (lane < k) {
+      if (P.knn_idx) P.knn_idx[gi * k + lane] = (ej == INT_MAX) ? -1 : ej;
+      if (P.knn_dist) P.knn_dist[gi * k + lane] = ed;
+    }
+  }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -515,9 +608,43 @@ int launch_pairs(int flags, unsigned grid, size_t smem, cudaStream_t st, const C
   return DBB_ERR_INVALID;
 }
 
+// Wave quantisation: with one CTA per SM, n_rt row sweeps take ceil(n_rt / SMs) rounds.  The row tiles of the
+// last, partial round are split into n_seg column segments so that the leftover work spreads over all SMs;
+// items are handed out dynamically, whole sweeps first (longest-processing-time order).
+void plan_items(int64_t n_rt, int64_t n_ct, int sms, int64_t* n_full_out, int64_t* rem_out, int* n_seg_out) {
+  int64_t n_full = (n_rt / sms) * sms, rem = n_rt - n_full;
+  int n_seg = 1;
+  if (rem > 0) {
+    double best = 1e30;
+    const int max_seg = (int)std::min<int64_t>(8, std::max<int64_t>(1, n_ct / 8));   // keep segments >= 8 column tiles
+    for (int sg = 1; sg <= max_seg; ++sg) {
+      const double rounds = (double)((rem * sg + sms - 1) / sms) / sg + 0.02 * (sg - 1);   // + flood/merge overhead per split
+      if (rounds < best - 1e-9) { best = rounds; n_seg = sg; }
+    }
+    const char* env_seg = getenv("DBB_K2_SEG");      // tests force a split on small inputs
+    if (env_seg && *env_seg) n_seg = std::max(1, std::min(atoi(env_seg), (int)std::max<int64_t>(1, n_ct)));
+  }
+  if (n_seg == 1) { n_full = n_rt; rem = 0; }
+  *n_full_out = n_full; *rem_out = rem; *n_seg_out = n_seg;
+}
+
 }  // namespace
 
-DBB_EXPORT int64_t dbb_pairs_scratch_bytes(int64_t, int64_t, int32_t) { return 0; }
+DBB_EXPORT int64_t dbb_pairs_scratch_bytes(int64_t n, int64_t rows, int32_t k) {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int64_t n_full, rem; int n_seg;
+  plan_items((rows + TILE - 1) / TILE, (n + TILE - 1) / TILE, sms, &n_full, &rem, &n_seg);
+  return 256 + rem * TILE * n_seg * ((int64_t)std::max(k, 1) * 8 + 16);
+}
+
+DBB_EXPORT int dbb_pairs_launches(int64_t n, int64_t rows) {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int64_t n_full, rem; int n_seg;
+  plan_items((rows + TILE - 1) / TILE, (n + TILE - 1) / TILE, sms, &n_full, &rem, &n_seg);
+  return rem > 0 ? 2 : 1;
+}
 
 DBB_EXPORT int dbb_pairs_dev(const dbb_pairs_input* in, int64_t row0, int64_t row1, const dbb_pairs_output* out,
                              void* stream) {
@@ -559,9 +686,41 @@ DBB_EXPORT int dbb_pairs_dev(const dbb_pairs_input* in, int64_t row0, int64_t ro
   int dev = 0, sms = 0;
   DBB_CUDA_TRY(cudaGetDevice(&dev));
   DBB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const size_t smem = sizeof(SmemLayout) + 128;
-  const int64_t n_rt = (row1 - row0 + TILE - 1) / TILE;
-  const unsigned grid = (unsigned)std::min<int64_t>(n_rt, sms);
+  const size_t smem = sizeof(SmemLayout);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n_rows = row1 - row0;
+  const int64_t n_rt = (n_rows + TILE - 1) / TILE;
+  const int64_t n_ct = (in->n + TILE - 1) / TILE;
+
+  int64_t n_full, rem;
+  int n_seg;
+  plan_items(n_rt, n_ct, sms, &n_full, &rem, &n_seg);
+  P.n_full_rt = (int32_t)n_full;
+  P.n_seg = n_seg;
+  P.n_items = (int32_t)(n_full + rem * n_seg);
+  const int64_t split_rows = std::min<int64_t>(rem * TILE, n_rows - n_full * TILE);
+  const size_t k_ = (size_t)std::max(out->k, 1);
+  size_t off_idx = 256, off_dist, off_cnt, off_bp, total;
+  off_dist = off_idx + (size_t)rem * TILE * n_seg * k_ * 4;
+  off_cnt = off_dist + (size_t)rem * TILE * n_seg * k_ * 4;
+  off_bp = (off_cnt + (size_t)rem * TILE * n_seg * 4 + 7) & ~(size_t)7;
+  total = off_bp + (size_t)rem * TILE * n_seg * 8;
+  uint8_t* scratch = nullptr;
+  DBB_CUDA_TRY(cudaMallocAsync((void**)&scratch, total, st));
+  DBB_CUDA_TRY(cudaMemsetAsync(scratch, 0, 256, st));
+  P.item_counter = (uint32_t*)scratch;
+  P.part_idx = (int32_t*)(scratch + off_idx);
+  P.part_dist = (float*)(scratch + off_dist);
+  P.part_cnt = (int32_t*)(scratch + off_cnt);
+  P.part_bp = (int64_t*)(scratch + off_bp);
+
+  const unsigned grid = (unsigned)std::min<int64_t>(P.n_items, sms);
   const int flags = (in->td_bound ? 1 : 0) | ((in->gc || in->cov) ? 2 : 0) | (masks ? 4 : 0) | (out->k > 0 ? 8 : 0);
-  return launch_pairs(flags, grid, smem, (cudaStream_t)stream, tmap, P);
+  rc = launch_pairs(flags, grid, smem, st, tmap, P);
+  if (rc == DBB_OK && rem > 0 && split_rows > 0) {
+    merge_kernel<<<(unsigned)((split_rows + 3) / 4), 128, 0, st>>>(P, n_full * TILE, split_rows);
+    if (cudaGetLastError() != cudaSuccess) { dbb::set_error("merge kernel launch failed"); rc = DBB_ERR_CUDA; }
+  }
+  cudaFreeAsync(scratch, st);
+  return rc;
 }

@@ -137,8 +137,10 @@ typedef struct {
  * pointers.  Enqueues on `stream`. */
 int dbb_pairs_dev(const dbb_pairs_input* in, int64_t row0, int64_t row1, const dbb_pairs_output* out,
                   void* stream);
-/* bytes of device scratch dbb_pairs_dev needs internally for (n, rows, k) -- informational */
+/* bytes of stream-ordered device scratch dbb_pairs_dev allocates internally for (n, rows, k), and the number
+ * of kernels it launches (pair kernel + merge of column-split row tiles) -- informational */
 int64_t dbb_pairs_scratch_bytes(int64_t n, int64_t rows, int32_t k);
+int dbb_pairs_launches(int64_t n, int64_t rows);
 /* same with HOST pointers everywhere (sig is dense [n][136] float32 on the host) */
 int dbb_pairs_host(const dbb_pairs_input* in_host, int64_t row0, int64_t row1,
                    const dbb_pairs_output* out_host);

@@ -127,3 +127,22 @@ def test_small_and_degenerate_inputs():
         m = util.unpack_mask(r['td_mask'], n)
         assert (np.diag(m) == 1).all()                     # i == j is always a TD neighbour (0 < bound)
         assert np.array_equal(r['count'], m.sum(axis=1))
+
+
+def test_column_split_items_merge_to_identical_results(monkeypatch):
+    """Row tiles of the last partial wave are split into column segments and merged (csrc/pairs.cu
+    plan_items / merge_kernel); forcing a 3-way split on a small input must not change any output."""
+    from dbb_b200 import _pairs
+    from dbb_b200.distributions import PairTables
+    meta, sig64 = _metagenome(23, 1500, gmax=12000)
+    td, gcd, cvd = _dists()
+    tables = PairTables(meta.length, GC=meta.gc_obs, coverage=meta.coverage, tdDist=td, tdDistPer=80, gcDist=gcd,
+                        gcDistPer=80, covDist=cvd, covDistPer=80)
+    kw = dict(k=20, topk_filter=_pairs.FILTER_GC, want_count=True, want_td_mask=True)
+    monkeypatch.setenv('DBB_K2_SEG', '1')
+    whole = _pairs.run_pairs_host(sig64, tables, **kw)
+    for seg in ('2', '3', '5'):
+        monkeypatch.setenv('DBB_K2_SEG', seg)
+        split = _pairs.run_pairs_host(sig64, tables, **kw)
+        for key in whole:
+            assert np.array_equal(whole[key], split[key]), (seg, key)
