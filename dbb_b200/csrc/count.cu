@@ -47,78 +47,76 @@ __device__ __forceinline__ void group_sync() {
   if (THREADS == 32) __syncwarp(); else __syncthreads();
 }
 
-__device__ __forceinline__ void red_inc_if(uint32_t smem_addr, uint32_t mask_word, uint32_t bit) {
-  asm volatile(
-      "{\n\t.reg .pred q;\n\t.reg .b32 t;\n\t"
-      "and.b32 t, %1, %2;\n\t"
-      "setp.ne.b32 q, t, 0;\n\t"
-      "@q red.shared.add.u32 [%0], 1;\n\t}"
-      :: "r"(smem_addr), "r"(mask_word), "r"(bit) : "memory");
-}
-
-// Update the histograms with one 64-base block.
-//   w[0..3]: code words of the block, w[4]: first code word of the next block (halo)
-//   V: validity of the 64 bases (bit 63-p), Vh: validity of the next block's first 32 bases (bit 31-p)
-//   hS: shared address of the (3+S)-mer histogram, c4: shared address of the 256-bin tetramer histogram
+// Rare path: blocks that are not fully valid (N / IUPAC / lowercase, the padded last block of a scaffold, a
+// block whose halo is invalid).  The warp handles them one at a time and COOPERATIVELY: the owning lane
+// publishes the block through a 10-word shared scratch, lane a then treats anchor a (a, a+32 for S = 1).  A
+// fully valid anchor still updates the (3+S)-mer histogram; otherwise its valid windows go one by one to the
+// tetramer histogram.  ~60 instructions per slow block instead of ~1000 for a per-lane loop over anchors.
 template <int S>
-__device__ __forceinline__ void process_block(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3,
-                                              uint32_t w4, uint64_t V, uint32_t Vh, int n_anchor,
-                                              uint32_t hS, uint32_t c4) {
+__device__ __noinline__ void slow_blocks(uint32_t slowmask, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3,
+                                         uint32_t w4, uint64_t V, uint32_t Vh, int n_anchor,
+                                         volatile uint32_t* sc, uint32_t* hS, uint32_t* c4, int lane) {
   constexpr int R = S + 3;
   constexpr int KB = 2 * R;
-  constexpr uint32_t BINMASK4 = ((1u << KB) - 1u) << 2;
-  const uint32_t w[5] = {w0, w1, w2, w3, w4};
-
-  // wv bit (63-p): the 4 bases p..p+3 are valid; sv: the R bases p..p+R-1 are valid
-  uint64_t wv = V;
-  #pragma unroll
-  for (int t = 1; t < 4; ++t) wv &= (V << t) | (uint64_t)(Vh >> (32 - t));
-  uint64_t sv = wv;
-  #pragma unroll
-  for (int t = 4; t < R; ++t) sv &= (V << t) | (uint64_t)(Vh >> (32 - t));
-  if (S == 3 && n_anchor < 22) sv &= ~1ull;            // anchor 63 belongs to the next block
-  const uint32_t sv_hi = (uint32_t)(sv >> 32), sv_lo = (uint32_t)sv;
-
-  #pragma unroll
-  for (int p = 0; p < 64; p += S) {
-    const int k = p >> 4, o = p & 15;
-    const int sh = 64 - 2 * o - KB - 2;                // >= 18
-    uint32_t x = (sh >= 32) ? (w[k] >> (sh - 32)) : __funnelshift_r(w[k + 1], w[k], sh);
-    uint32_t off = x & BINMASK4;
-    if (p < 32) red_inc_if(hS + off, sv_hi, 1u << (31 - p));
-    else        red_inc_if(hS + off, sv_lo, 1u << (63 - p));
-  }
-
-  if (S > 1) {
-    // anchors whose super-k-mer is not fully valid but which still own >= 1 valid window
-    uint32_t wvh = Vh & (Vh << 1) & (Vh << 2) & (Vh << 3);
-    uint64_t anyw = wv;
-    #pragma unroll
-    for (int t = 1; t < S; ++t) anyw |= (wv << t) | (uint64_t)(wvh >> (32 - t));
-    uint64_t anchors = 0;
-    #pragma unroll
-    for (int p = 0; p < 64; p += S) anchors |= 1ull << (63 - p);
-    if (S == 3 && n_anchor < 22) anchors &= ~1ull;
-    uint64_t need = ~sv & anchors & anyw;
-    if (need != 0) {
-      #pragma unroll
-      for (int p = 0; p < 64; p += S) {
-        if ((need >> (63 - p)) & 1ull) {
-          #pragma unroll
-          for (int o2 = 0; o2 < S; ++o2) {
-            const int q = p + o2;
-            bool ok = (q < 64) ? ((wv >> (63 - q)) & 1ull) : ((wvh >> (31 - (q - 64))) & 1u);
-            if (ok) {
-              const int k = q >> 4, o = q & 15;
-              const int sh = 64 - 2 * o - 8 - 2;
-              uint32_t x = (sh >= 32) ? (w[k] >> (sh - 32)) : __funnelshift_r(w[k + 1], w[k], sh);
-              asm volatile("red.shared.add.u32 [%0], 1;" :: "r"(c4 + (x & 0x3FCu)) : "memory");
-            }
+  while (slowmask) {
+    const int src = __ffs(slowmask) - 1;
+    slowmask &= slowmask - 1;
+    if (lane == src) {
+      sc[0] = w0; sc[1] = w1; sc[2] = w2; sc[3] = w3; sc[4] = w4; sc[5] = 0u;
+      sc[6] = (uint32_t)(V >> 32); sc[7] = (uint32_t)V; sc[8] = Vh; sc[9] = (uint32_t)n_anchor;
+    }
+    __syncwarp();
+    const uint64_t V64 = ((uint64_t)sc[6] << 32) | sc[7];
+    const uint32_t vh = sc[8];
+    const int na = (int)sc[9];
+    for (int a = lane; a < na; a += 32) {
+      const int p = a * S;
+      // validity of positions p, p+1, ... in the top bits of x
+      const uint64_t x = (V64 << p) | (p ? (((uint64_t)vh << 32) >> (64 - p)) : 0ull);
+      const int k = p >> 4, o = p & 15;
+      if ((x >> (64 - R)) == ((1ull << R) - 1ull)) {
+        const uint64_t pair = ((uint64_t)sc[k] << 32) | sc[k + 1];
+        atomicAdd(&hS[(uint32_t)(pair >> (64 - 2 * o - KB)) & ((1u << KB) - 1u)], 1u);
+      } else {
+        #pragma unroll
+        for (int o2 = 0; o2 < S; ++o2) {
+          if (((x >> (60 - o2)) & 15ull) == 15ull) {
+            const int q = p + o2, k2 = q >> 4, oq = q & 15;
+            const uint64_t pair = ((uint64_t)sc[k2] << 32) | sc[k2 + 1];
+            atomicAdd(&c4[(uint32_t)(pair >> (64 - 2 * oq - 8)) & 255u], 1u);
           }
         }
       }
     }
+    __syncwarp();
   }
+}
+
+// Fast path of one 64-base block whose bases (and the R-1 halo bases) are all valid: one unpredicated
+// shared-memory atomic per anchor -- funnel shift, mask, ATOMS: 3 instructions per S windows.
+//   w0..w3: code words of the block, w4: first code word of the next block (halo)
+//   n_anchor: super-k-mers anchored in this block (64/S; 21 or 22 for S = 3)
+template <int S>
+__device__ __forceinline__ void fast_block(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4,
+                                           int n_anchor, uint32_t* hS) {
+  constexpr int KB = 2 * (S + 3);
+  constexpr uint32_t BINMASK4 = ((1u << KB) - 1u) << 2;
+  constexpr int NA = (64 + S - 1) / S;                 // 64, 32, 22, 16
+  const uint32_t w[5] = {w0, w1, w2, w3, w4};
+  #pragma unroll
+  for (int p = 0; p < 64; p += S) {
+    const int k = p >> 4, o = p & 15;
+    const int sh = 64 - 2 * o - KB - 2;                // >= 18
+    const uint32_t x = (sh >= 32) ? (w[k] >> (sh - 32)) : __funnelshift_r(w[k + 1], w[k], sh);
+    if (S == 3 && p == 63 && n_anchor != NA) continue; // S = 3: the anchor at 63 may belong to the next block
+    atomicAdd(reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(hS) + (x & BINMASK4)), 1u);
+  }
+}
+
+template <int S>
+__device__ __forceinline__ bool block_all_valid(uint64_t V, uint32_t Vh) {
+  constexpr uint32_t HALO = ~0u << (32 - (S + 2));     // the R-1 halo bases an anchor of this block may touch
+  return (V == ~0ull) && ((Vh & HALO) == HALO);
 }
 
 template <int S, int THREADS>
@@ -135,70 +133,122 @@ __global__ void __launch_bounds__(THREADS) count_kernel(const Item* __restrict__
   uint32_t* hS = (S == 1) ? smem : smem + 256;           // [BINS] (aliases c4 when S == 1)
   __shared__ uint32_t s_item;
   __shared__ uint32_t s_total[THREADS / 32];
+  __shared__ uint32_t s_slow[THREADS / 32][10];
   const int tid = threadIdx.x, lane = tid & 31;
-  const uint32_t c4_addr = (uint32_t)__cvta_generic_to_shared(c4);
-  const uint32_t hS_addr = (uint32_t)__cvta_generic_to_shared(hS);
 
   for (int i = tid; i < (S == 1 ? 256 : 256 + BINS); i += THREADS) smem[i] = 0;
   group_sync<THREADS>();
 
-  while (true) {
-    if (tid == 0) s_item = atomicAdd(next_item, 1u);
-    group_sync<THREADS>();
-    const uint32_t it = s_item;
-    if (it >= n_items) break;
-    const Item item = items[it];
-    const uint32_t nb = item.n_blocks;
-    const bool last_chunk = (item.flags & ITEM_LAST) != 0;
-    const uint32_t slot = item.flags & ITEM_SLOT_MASK;
-    const uint32_t first_mod3 = (item.flags >> 29) & 3u;
-    const uint4* cp = codes + item.blk_begin;
-    const uint64_t* vp = valid + item.blk_begin;
-
-    for (uint32_t base = 0; base < nb; base += THREADS) {
-      const uint32_t b = base + tid;
-      const bool act = b < nb;
-      uint4 c = make_uint4(0, 0, 0, 0);
-      uint64_t V = 0;
-      if (act) { c = __ldg(cp + b); V = __ldg(vp + b); }
-      uint32_t hw = __shfl_down_sync(0xffffffffu, c.x, 1);
-      uint32_t hv = __shfl_down_sync(0xffffffffu, (uint32_t)(V >> 32), 1);
-      if (act && (lane == 31 || b + 1 == nb)) {
-        const bool has = (b + 1 < nb) || !last_chunk;
-        hw = has ? __ldg(reinterpret_cast<const uint32_t*>(cp + b + 1)) : 0u;
-        hv = has ? (uint32_t)(__ldg(vp + b + 1) >> 32) : 0u;
-      }
-      if (act) {
-        if (S == 3) {
-          // anchors are the positions P = 0 mod 3 counted from the scaffold start; rotate the block so
-          // that its first anchor sits at bit position 0
-          const uint32_t bs = (first_mod3 + b) % 3u;          // (block index within scaffold) mod 3
-          const uint32_t p0 = (3u - bs) % 3u;                 // 64 = 1 mod 3
-          const uint32_t r2 = 2 * p0;
-          uint32_t w0 = __funnelshift_l(c.y, c.x, r2), w1 = __funnelshift_l(c.z, c.y, r2);
-          uint32_t w2 = __funnelshift_l(c.w, c.z, r2), w3 = __funnelshift_l(hw, c.w, r2);
-          uint32_t w4 = hw << r2;
-          uint64_t V2 = (V << p0) | (uint64_t)(p0 ? (hv >> (32 - p0)) : 0u);
-          uint32_t hv2 = hv << p0;
-          process_block<S>(w0, w1, w2, w3, w4, V2, hv2, p0 == 0 ? 22 : 21, hS_addr, c4_addr);
-        } else {
-          process_block<S>(c.x, c.y, c.z, c.w, hw, V, hv, 64 / S, hS_addr, c4_addr);
+  // Static schedule: CTA b takes items b, b + grid, ... of a list sorted by descending size, so every load of
+  // the pipeline below is known one step ahead: the first block of the NEXT item is requested before the
+  // current item is flushed, the next iteration's blocks before the current ones are processed.
+  struct Fetch { uint4 c; uint64_t V; uint32_t hw, hv; };
+  auto fetch = [&](const Item& im, uint32_t b) {
+    Fetch f;
+    f.c = make_uint4(0, 0, 0, 0); f.V = 0; f.hw = 0; f.hv = 0;
+    if (b < im.n_blocks) {
+      f.c = __ldg(codes + im.blk_begin + b);
+      f.V = __ldg(valid + im.blk_begin + b);
+      // the halo normally comes from the next lane; the last lane / last block fetches its own
+      if (lane == 31 || b + 1 == im.n_blocks) {
+        const bool has = (b + 1 < im.n_blocks) || !(im.flags & ITEM_LAST);
+        if (has) {
+          f.hw = __ldg(reinterpret_cast<const uint32_t*>(codes + im.blk_begin + b + 1));
+          f.hv = (uint32_t)(__ldg(valid + im.blk_begin + b + 1) >> 32);
         }
       }
+    }
+    return f;
+  };
+  (void)next_item; (void)s_item;
+  uint32_t it = blockIdx.x;
+  Item item = Item{0, 0, 0, 0};
+  Fetch nxt;
+  nxt.c = make_uint4(0, 0, 0, 0); nxt.V = 0; nxt.hw = 0; nxt.hv = 0;
+  if (it < n_items) { item = items[it]; nxt = fetch(item, tid); }
+
+  while (it < n_items) {
+    const uint32_t it_n = it + gridDim.x;
+    const bool has_n = it_n < n_items;
+    Item item_n = Item{0, 0, 0, 0};
+    if (has_n) item_n = items[it_n];
+    const uint32_t nb = item.n_blocks;
+    const uint32_t slot = item.flags & ITEM_SLOT_MASK;
+    const uint32_t first_mod3 = (item.flags >> 29) & 3u;
+
+    for (uint32_t base = 0; base < nb || base == 0; base += THREADS) {
+      const uint32_t b = base + tid;
+      const bool act = b < nb;
+      const Fetch cur = nxt;
+      if (base + THREADS < nb) nxt = fetch(item, base + THREADS + tid);
+      else if (has_n) nxt = fetch(item_n, tid);
+      const uint4 c = cur.c;
+      const uint64_t V = cur.V;
+      uint32_t hw = __shfl_down_sync(0xffffffffu, c.x, 1);
+      uint32_t hv = __shfl_down_sync(0xffffffffu, (uint32_t)(V >> 32), 1);
+      if (lane == 31 || b + 1 >= nb) { hw = cur.hw; hv = cur.hv; }
+      uint32_t w0 = c.x, w1 = c.y, w2 = c.z, w3 = c.w, w4 = hw;
+      uint64_t Vb = V;
+      uint32_t hvb = hv;
+      int n_anchor = (64 + S - 1) / S;
+      if (S == 3) {
+        // anchors are the positions P = 0 mod 3 counted from the scaffold start; rotate the block so that
+        // its first anchor sits at bit position 0
+        const uint32_t bs = (first_mod3 + b) % 3u;            // (block index within scaffold) mod 3
+        const uint32_t p0 = (3u - bs) % 3u;                   // 64 = 1 mod 3
+        const uint32_t r2 = 2 * p0;
+        w0 = __funnelshift_l(c.y, c.x, r2); w1 = __funnelshift_l(c.z, c.y, r2);
+        w2 = __funnelshift_l(c.w, c.z, r2); w3 = __funnelshift_l(hw, c.w, r2);
+        w4 = hw << r2;
+        Vb = (V << p0) | (uint64_t)(p0 ? (hv >> (32 - p0)) : 0u);
+        hvb = hv << p0;
+        n_anchor = p0 == 0 ? 22 : 21;
+      }
+      const bool ok = act && block_all_valid<S>(Vb, hvb);
+      if (ok) fast_block<S>(w0, w1, w2, w3, w4, n_anchor, hS);
+      const uint32_t slow = __ballot_sync(0xffffffffu, act && !ok);
+      if (slow) slow_blocks<S>(slow, w0, w1, w2, w3, w4, Vb, hvb, n_anchor, s_slow[tid >> 5], hS, c4, lane);
     }
     group_sync<THREADS>();
 
     if (S > 1) {
-      // fold the (3+S)-mer histogram into the 256 tetramer codes, re-zeroing it on the way
-      for (int x = tid; x < BINS; x += THREADS) {
-        uint32_t v = hS[x];
-        if (v) {
-          hS[x] = 0;
+      // Fold the (3+S)-mer histogram into the 256 tetramer codes: for window offset o the count of code c is
+      // the marginal over the o bases before and the S-1-o bases after it.  Thread <-> code, so no atomics
+      // are needed (two thread groups split the offsets when the CTA has >= 512 threads); runs of >= 4 bins
+      // are read as 128-bit words, rotated by the code so that neighbouring lanes hit different banks.
+      constexpr int NPART = THREADS >= 512 ? 2 : 1;
+      const int part = tid >> 8;
+      if (part < NPART) {
+        for (int c = tid & 255; c < 256; c += (THREADS < 256 ? THREADS : 256)) {
+          uint32_t sum = 0;
           #pragma unroll
-          for (int o = 0; o < S; ++o) atomicAdd(&c4[(x >> (2 * (S - 1 - o))) & 255], v);
+          for (int o = 0; o < S; ++o) {
+            if (NPART == 2 && (o & 1) != part) continue;
+            constexpr int dummy = 0; (void)dummy;
+            const int e = S - 1 - o;                  // bases after the window
+            const int run = 1 << (2 * e);             // consecutive bins per prefix value
+            const int np = 1 << (2 * o);              // prefix values
+            #pragma unroll
+            for (int pfx = 0; pfx < np; ++pfx) {
+              const int base = (pfx << (8 + 2 * e)) | (c << (2 * e));
+              if (run >= 4) {
+                const int nq = run >> 2;
+                #pragma unroll
+                for (int r4 = 0; r4 < nq; ++r4) {
+                  const uint4 v = *reinterpret_cast<const uint4*>(hS + base + 4 * ((r4 + c) & (nq - 1)));
+                  sum += (v.x + v.y) + (v.z + v.w);
+                }
+              } else {
+                sum += hS[base];
+              }
+            }
+          }
+          if (NPART == 2) atomicAdd(&c4[c], sum); else c4[c] += sum;
         }
       }
       group_sync<THREADS>();
+      for (int x = tid * 4; x < BINS; x += THREADS * 4) *reinterpret_cast<uint4*>(hS + x) = make_uint4(0, 0, 0, 0);
+      // (the next item's first update is behind the two group_syncs below)
     }
 
     // total, then canonical fold 256 -> 136 and output
@@ -239,6 +289,8 @@ __global__ void __launch_bounds__(THREADS) count_kernel(const Item* __restrict__
     group_sync<THREADS>();
     for (int i = tid; i < 256; i += THREADS) c4[i] = 0;
     group_sync<THREADS>();
+    it = it_n;
+    item = item_n;
   }
 }
 
@@ -285,6 +337,9 @@ struct dbb_count_plan {
   uint32_t* d_split_counts = nullptr;
   int sm_count = 0;
   int launches = 0;
+  // the four class kernels run concurrently on their own streams so that the tail of one overlaps the others
+  cudaStream_t class_stream[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 namespace {
@@ -343,9 +398,9 @@ DBB_EXPORT int dbb_count_plan_create(const int64_t* h_blk_off, int64_t n_seq, db
   cudaDeviceGetAttribute(&plan->sm_count, cudaDevAttrMultiProcessorCount, dev);
 
   // class thresholds in blocks (64 bases); env overrides are for tuning runs only
-  const int64_t t1 = env_i64("DBB_K1_T1", 40);          // <= 2.5 kb  : S = 1, one warp per scaffold
-  const int64_t t2 = env_i64("DBB_K1_T2", 320);         // <= 20 kb   : S = 2
-  const int64_t t3 = env_i64("DBB_K1_T3", 3072);        // <= 196 kb  : S = 3
+  const int64_t t1 = env_i64("DBB_K1_T1", 44);          // <= 2.8 kb  : S = 1, one warp per scaffold
+  const int64_t t2 = env_i64("DBB_K1_T2", 512);         // <= 33 kb   : S = 2
+  const int64_t t3 = env_i64("DBB_K1_T3", 4300);        // <= 275 kb  : S = 3
   const int64_t chunk = env_i64("DBB_K1_CHUNK", 16384); // S = 4 chunk: 1 Mb
   std::vector<Item> cls[4];
   std::vector<uint32_t> split_scaffold;
@@ -385,6 +440,11 @@ DBB_EXPORT int dbb_count_plan_create(const int64_t* h_blk_off, int64_t n_seq, db
     if (e == cudaSuccess) e = cudaMemcpy(plan->d_items, all.data(), all.size() * sizeof(Item), cudaMemcpyHostToDevice);
   }
   if (e == cudaSuccess) e = cudaMalloc(&plan->d_counters, 4 * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&plan->ev_fork, cudaEventDisableTiming);
+  for (int c = 0; c < 4 && e == cudaSuccess; ++c) {
+    e = cudaStreamCreateWithFlags(&plan->class_stream[c], cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&plan->ev_join[c], cudaEventDisableTiming);
+  }
   if (e == cudaSuccess && plan->n_split) {
     e = cudaMalloc(&plan->d_split_scaffold, plan->n_split * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMemcpy(plan->d_split_scaffold, split_scaffold.data(), plan->n_split * sizeof(uint32_t), cudaMemcpyHostToDevice);
@@ -405,6 +465,11 @@ DBB_EXPORT int dbb_count_plan_destroy(dbb_count_plan* plan) {
   cudaFree(plan->d_counters);
   cudaFree(plan->d_split_scaffold);
   cudaFree(plan->d_split_counts);
+  for (int c = 0; c < 4; ++c) {
+    if (plan->class_stream[c]) cudaStreamDestroy(plan->class_stream[c]);
+    if (plan->ev_join[c]) cudaEventDestroy(plan->ev_join[c]);
+  }
+  if (plan->ev_fork) cudaEventDestroy(plan->ev_fork);
   delete plan;
   return DBB_OK;
 }
@@ -423,12 +488,28 @@ DBB_EXPORT int dbb_tetra_count_dev(dbb_count_plan* plan, const void* d_codes, co
   DBB_CUDA_TRY(cudaMemsetAsync(plan->d_counters, 0, 4 * sizeof(uint32_t), st));
   if (plan->n_split)
     DBB_CUDA_TRY(cudaMemsetAsync(plan->d_split_counts, 0, (size_t)plan->n_split * DBB_NUM_KMERS * sizeof(uint32_t), st));
-  int rc;
-  // longest-running class first
-  if ((rc = launch_class<4, 512>(plan, 3, d_codes, d_valid, d_counts, d_freq, freq_stride, st)) != DBB_OK) return rc;
-  if ((rc = launch_class<3, 256>(plan, 2, d_codes, d_valid, d_counts, d_freq, freq_stride, st)) != DBB_OK) return rc;
-  if ((rc = launch_class<2, 64>(plan, 1, d_codes, d_valid, d_counts, d_freq, freq_stride, st)) != DBB_OK) return rc;
-  if ((rc = launch_class<1, 32>(plan, 0, d_codes, d_valid, d_counts, d_freq, freq_stride, st)) != DBB_OK) return rc;
+  // fork: every class kernel on its own stream behind the memsets, join back into the caller's stream
+  DBB_CUDA_TRY(cudaEventRecord(plan->ev_fork, st));
+  int rc = DBB_OK;
+  for (int c = 3; c >= 0 && rc == DBB_OK; --c) {            // longest-running class first
+    if (plan->class_count[c] == 0) continue;
+    cudaStream_t cs = plan->class_stream[c];
+    DBB_CUDA_TRY(cudaStreamWaitEvent(cs, plan->ev_fork, 0));
+    // CTA sizes: env overrides exist for tuning sweeps (profiles/), the defaults are the measured best
+    static const int thr4 = (int)env_i64("DBB_K1_THR4", 512), thr3 = (int)env_i64("DBB_K1_THR3", 256),
+                     thr2 = (int)env_i64("DBB_K1_THR2", 64);
+#define DBB_LAUNCH(S_, T_) rc = launch_class<S_, T_>(plan, c, d_codes, d_valid, d_counts, d_freq, freq_stride, cs)
+    switch (c) {
+      case 3: if (thr4 >= 1024) DBB_LAUNCH(4, 1024); else DBB_LAUNCH(4, 512); break;
+      case 2: if (thr3 >= 512) DBB_LAUNCH(3, 512); else if (thr3 >= 256) DBB_LAUNCH(3, 256); else DBB_LAUNCH(3, 128); break;
+      case 1: if (thr2 >= 256) DBB_LAUNCH(2, 256); else if (thr2 >= 128) DBB_LAUNCH(2, 128); else DBB_LAUNCH(2, 64); break;
+      default: DBB_LAUNCH(1, 32); break;
+    }
+#undef DBB_LAUNCH
+    if (rc != DBB_OK) return rc;
+    DBB_CUDA_TRY(cudaEventRecord(plan->ev_join[c], cs));
+    DBB_CUDA_TRY(cudaStreamWaitEvent(st, plan->ev_join[c], 0));
+  }
   if (plan->n_split) {
     finalize_kernel<<<plan->n_split, 160, 0, st>>>(plan->d_split_counts, plan->d_split_scaffold, plan->n_split,
                                                    d_counts, d_freq, freq_stride);
