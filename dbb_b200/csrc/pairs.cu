@@ -41,7 +41,7 @@ constexpr int NSTAGE = 4;
 constexpr int CHUNK_BYTES = TILE * KCH * 4;  // 14336
 constexpr int COMPUTE_WARPS = 8;
 constexpr int THREADS = COMPUTE_WARPS * 32;       // 8 warps: register allocation is per 4 warps
-constexpr int PREFETCH = NSTAGE - 2;             // B chunks in flight ahead of the consumer
+constexpr int PREFETCH = 2;                  // B chunks in flight ahead of the consumers
 constexpr int LIST_K = DBB_MAX_K;            // list slots per row
 constexpr int QCAP = 512;                    // queue entries per warp (>= 2 x the 256 pushes of one row pair)
 
@@ -64,7 +64,7 @@ struct Params {
   uint32_t* td_mask; uint32_t* gc_mask; uint32_t* cov_mask; int64_t mask_words;
   // work items: row tiles [0, n_full_rt) are swept over all columns by one CTA; each remaining row tile is
   // split into n_seg column segments (separate items) whose partial results are merged afterwards
-  int32_t n_full_rt, n_seg, n_items;
+  int32_t n_full_rt, n_seg, n_items, debug_skip_epilogue;
   uint32_t* item_counter;
   int32_t* part_idx; float* part_dist; int32_t* part_cnt; int64_t* part_bp;
 };
@@ -74,18 +74,21 @@ struct SmemLayout {
   alignas(128) float b[NSTAGE][TILE][KCH];
   float list_d[TILE][LIST_K];
   int32_t list_j[TILE][LIST_K];
-  float scratch[COMPUTE_WARPS][8][32];   // distances of one row pair, handed to the flood path
   float qd[COMPUTE_WARPS][QCAP];         // per-warp queue of pairs that may be a neighbour or a top-k candidate
+                                         //   (the every-pair path reuses the first 256 entries as its scratch)
   uint32_t qcode[COMPUTE_WARPS][QCAP];   //   (row within the warp's 16) << 7 | (column within the tile)
   RowScalars rows[TILE];
   uint32_t bp_lo[TILE], bp_hi[TILE];     // neighbourhood base pairs per row (64-bit as two native 32-bit atomics)
   int32_t cnt[TILE];                     // neighbourhood size per row
   float thr[TILE];                       // current k-th best distance per row (+inf until k found)
+  int32_t qn[COMPUTE_WARPS];             // queue fill per warp
   alignas(8) uint64_t full[NSTAGE];
   uint64_t empty[NSTAGE];
   uint64_t a_full;
   int32_t item;
 };
+
+static_assert(sizeof(SmemLayout) <= 232448, "SmemLayout exceeds the 227 KB per-CTA shared memory limit");
 
 // ---- mbarrier / TMA primitives ------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -160,7 +163,7 @@ __device__ __noinline__ void process_row_pair(SmemLayout& sm, const Params& P, i
   const int k = P.k;
   #pragma unroll 1
   for (int j = 0; j < 8; ++j) {
-    const float d = sm.scratch[warp][j][lane];
+    const float d = sm.qd[warp][j * 32 + lane];
     const int64_t cj = col_base + tx + 16 * j;
     const bool col_ok = cj < n;
     int32_t len_j = 0;
@@ -402,8 +405,8 @@ __global__ void __launch_bounds__(THREADS, 1) pairs_kernel(const __grid_constant
         mbar_wait(&sm.full[st], (q / NSTAGE) & 1);
         const float* ap = &sm.a[kc][warp * 16 + ty][0];
         const float* bq = &sm.b[st][tx][0];
-        // NOT unrolled: one k4 step is ~280 instructions (4.4 KB); unrolling all 7 made the loop 31 KB and
-        // instruction-fetch stalls ("no_instruction") cost ~25 % (profiles/r01_pairs_notes.md)
+        // NOT unrolled: one k4 step is ~280 instructions (4.4 KB).  Unrolling all 7 steps of a chunk (31 KB) cost
+        // ~25 % in instruction-fetch stalls; unrolling by two was 3 % slower than this (profiles/r01_pairs_notes.md).
         #pragma unroll 1
         for (int k4 = 0; k4 < KCH / 4; ++k4) {
           float4 av[8];
@@ -425,29 +428,59 @@ __global__ void __launch_bounds__(THREADS, 1) pairs_kernel(const __grid_constant
 
       // ---------------- epilogue of this column tile ----------------
       const int64_t col_base = (int64_t)ct * TILE;
-      if (always_slow || (F_TOPK && ct == ct0)) {
-        // flood tiles (every pair matters: masks, counts without a TD bound, or empty top-k lists)
+      if (P.debug_skip_epilogue) {
+        float keep = 0.f;
+        #pragma unroll
+        for (int i = 0; i < 8; ++i)
+          #pragma unroll
+          for (int j = 0; j < 8; ++j) keep += acc[i][j].x + acc[i][j].y;
+        if (keep == -1.f) sm.thr[0] = keep;
+      } else if (always_slow) {
+        // every pair matters (masks, or counts without a TD bound): evaluate all of them
         #pragma unroll
         for (int i = 0; i < 8; ++i) {
           #pragma unroll
-          for (int j = 0; j < 8; ++j) sm.scratch[warp][j][lane] = acc[i][j].x + acc[i][j].y;
+          for (int j = 0; j < 8; ++j) sm.qd[warp][j * 32 + lane] = acc[i][j].x + acc[i][j].y;
           __syncwarp();
           process_row_pair<FLAGS>(sm, P, warp, lane, warp * 16 + 2 * i, row_base, col_base);
         }
       } else {
-        // steady state: a pair is queued only if it can be a TD neighbour (d below the larger of the two
-        // bounds -- the exact rule is re-applied in the drain) or can enter the row's top-k (d <= k-th best)
+        // A pair is queued only if it can be a TD neighbour (d below the larger of the two bounds -- the exact
+        // rule is re-applied in the drain) or can enter the row's top-k (d <= k-th best).  On the first tile of
+        // a sweep the lists are empty; instead of flooding them with all 128 columns the threshold is the
+        // largest of the 16 lanes' m-th smallest distances, m = ceil((k+1)/16): at least k+1 columns pass.
+        const bool first_tile = F_TOPK && ct == ct0;
         float tdb_c[8];
+        bool col_ok[8];
         #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int64_t cj = col_base + tx + 16 * j;
-          tdb_c[j] = (F_TD && cj < n) ? __ldg(P.td_bound + cj) : -INFINITY;
+          col_ok[j] = cj < n;
+          tdb_c[j] = (F_TD && col_ok[j]) ? __ldg(P.td_bound + cj) : -INFINITY;
         }
-        int qn = 0;
+        if (lane == 0) sm.qn[warp] = 0;
+        __syncwarp();
         #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int lr = warp * 16 + 2 * i + ty;
-          const float u = fmaxf(F_TD ? sm.rows[lr].tdb : -INFINITY, sm.thr[lr]);
+          float thr_i = F_TOPK ? sm.thr[lr] : -INFINITY;
+          if (first_tile) {
+            const int m = (P.k + 16) / 16;                       // 1, 2 or 3
+            float m1 = INFINITY, m2 = INFINITY, m3 = INFINITY;   // the lane's three smallest valid distances
+            #pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float d = acc[i][j].x + acc[i][j].y;
+              d = (col_ok[j] && d == d) ? d : INFINITY;
+              const float t1 = fminf(m1, d), c1 = fmaxf(m1, d);
+              const float t2 = fminf(m2, c1), c2 = fmaxf(m2, c1);
+              m1 = t1; m2 = t2; m3 = fminf(m3, c2);
+            }
+            float tau = m == 1 ? m1 : (m == 2 ? m2 : m3);
+            #pragma unroll
+            for (int o = 1; o < 16; o <<= 1) tau = fmaxf(tau, __shfl_xor_sync(0xffffffffu, tau, o));
+            thr_i = tau;
+          }
+          const float u = fmaxf(F_TD ? sm.rows[lr].tdb : -INFINITY, thr_i);
           uint32_t bits = 0;
           #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -455,17 +488,8 @@ __global__ void __launch_bounds__(THREADS, 1) pairs_kernel(const __grid_constant
             acc[i][j].x = d;
             bits |= (d <= fmaxf(u, tdb_c[j])) ? (1u << j) : 0u;
           }
-          if (__any_sync(0xffffffffu, bits != 0u)) {
-            // exclusive prefix sum of the per-lane hit counts -> queue slots
-            const int c = __popc(bits);
-            int incl = c;
-            #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-              const int t = __shfl_up_sync(0xffffffffu, incl, o);
-              if (lane >= o) incl += t;
-            }
-            int slot = qn + incl - c;
-            qn += __shfl_sync(0xffffffffu, incl, 31);
+          if (bits) {
+            int slot = atomicAdd(&sm.qn[warp], __popc(bits));    // reserve queue slots (hits are rare)
             #pragma unroll
             for (int j = 0; j < 8; ++j) {
               if (bits & (1u << j)) {
@@ -475,16 +499,16 @@ __global__ void __launch_bounds__(THREADS, 1) pairs_kernel(const __grid_constant
               }
             }
           }
-          if (qn > QCAP - 256) {
-            __syncwarp();
+          __syncwarp();
+          const int qn = sm.qn[warp];
+          if (qn > QCAP - 256) {                                 // one row pair pushes at most 256 entries
             drain_queue<FLAGS>(sm, P, warp, lane, qn, row_base, col_base);
-            qn = 0;
+            if (lane == 0) sm.qn[warp] = 0;
+            __syncwarp();
           }
         }
-        if (qn) {
-          __syncwarp();
-          drain_queue<FLAGS>(sm, P, warp, lane, qn, row_base, col_base);
-        }
+        const int qn = sm.qn[warp];
+        if (qn) drain_queue<FLAGS>(sm, P, warp, lane, qn, row_base, col_base);
       }
     }  // column tiles
 
@@ -698,6 +722,7 @@ DBB_EXPORT int dbb_pairs_dev(const dbb_pairs_input* in, int64_t row0, int64_t ro
   P.n_full_rt = (int32_t)n_full;
   P.n_seg = n_seg;
   P.n_items = (int32_t)(n_full + rem * n_seg);
+  { const char* e2 = getenv("DBB_K2_DEBUG_SKIP_EPILOGUE"); P.debug_skip_epilogue = (e2 && *e2 == '1') ? 1 : 0; }   // profiling only
   const int64_t split_rows = std::min<int64_t>(rem * TILE, n_rows - n_full * TILE);
   const size_t k_ = (size_t)std::max(out->k, 1);
   size_t off_idx = 256, off_dist, off_cnt, off_bp, total;
@@ -705,6 +730,17 @@ DBB_EXPORT int dbb_pairs_dev(const dbb_pairs_input* in, int64_t row0, int64_t ro
   off_cnt = off_dist + (size_t)rem * TILE * n_seg * k_ * 4;
   off_bp = (off_cnt + (size_t)rem * TILE * n_seg * 4 + 7) & ~(size_t)7;
   total = off_bp + (size_t)rem * TILE * n_seg * 8;
+  // stream-ordered scratch; keep freed blocks cached in the device pool instead of returning them to the
+  // driver at every synchronisation (the default release threshold is 0)
+  static bool pool_configured = false;
+  if (!pool_configured) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    pool_configured = true;
+  }
   uint8_t* scratch = nullptr;
   DBB_CUDA_TRY(cudaMallocAsync((void**)&scratch, total, st));
   DBB_CUDA_TRY(cudaMemsetAsync(scratch, 0, 256, st));
