@@ -41,6 +41,7 @@ constexpr uint32_t ITEM_SLOT_MASK = (1u << 29) - 1;
 
 __constant__ int16_t c_col_code1[DBB_NUM_KMERS];
 __constant__ int16_t c_col_code2[DBB_NUM_KMERS];
+__constant__ int c_debug_skip_flush = 0;   // profiling switch (DBB_K1_DEBUG_SKIP_FLUSH=1): count only, no fold / output
 
 template <int THREADS>
 __device__ __forceinline__ void group_sync() {
@@ -161,6 +162,14 @@ __global__ void __launch_bounds__(THREADS) count_kernel(const Item* __restrict__
     return f;
   };
   (void)next_item; (void)s_item;
+  constexpr int NCOLT = (DBB_SIG_STRIDE + THREADS - 1) / THREADS;   // output columns per thread (136 + 4 padding)
+  int cc1[NCOLT], cc2[NCOLT];
+  #pragma unroll
+  for (int q = 0; q < NCOLT; ++q) {
+    const int col = tid + q * THREADS;
+    cc1[q] = col < DBB_NUM_KMERS ? c_col_code1[col] : -1;
+    cc2[q] = col < DBB_NUM_KMERS ? c_col_code2[col] : -1;
+  }
   uint32_t it = blockIdx.x;
   Item item = Item{0, 0, 0, 0};
   Fetch nxt;
@@ -210,6 +219,7 @@ __global__ void __launch_bounds__(THREADS) count_kernel(const Item* __restrict__
       if (slow) slow_blocks<S>(slow, w0, w1, w2, w3, w4, Vb, hvb, n_anchor, s_slow[tid >> 5], hS, c4, lane);
     }
     group_sync<THREADS>();
+    if (c_debug_skip_flush) { it = it_n; item = item_n; continue; }
 
     if (S > 1) {
       // Fold the (3+S)-mer histogram into the 256 tetramer codes: for window offset o the count of code c is
@@ -251,9 +261,18 @@ __global__ void __launch_bounds__(THREADS) count_kernel(const Item* __restrict__
       // (the next item's first update is behind the two group_syncs below)
     }
 
-    // total, then canonical fold 256 -> 136 and output
+    // canonical fold 256 -> 136 (column tables in registers), total = sum of the folded counts, one
+    // reciprocal per scaffold: freq = (float)(n * (1.0 / total))  (0 * inf = NaN when nothing was counted,
+    // as genomicSignatures.py:147-148 yields)
+    uint32_t nloc[NCOLT];
     uint32_t part = 0;
-    for (int i = tid; i < 256; i += THREADS) part += c4[i];
+    #pragma unroll
+    for (int q = 0; q < NCOLT; ++q) {
+      uint32_t nq = 0;
+      if (cc1[q] >= 0) { nq = c4[cc1[q]]; if (cc2[q] >= 0) nq += c4[cc2[q]]; }
+      nloc[q] = nq;
+      part += nq;
+    }
     #pragma unroll
     for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
     if (THREADS > 32) {
@@ -262,32 +281,28 @@ __global__ void __launch_bounds__(THREADS) count_kernel(const Item* __restrict__
       part = 0;
       #pragma unroll
       for (int i = 0; i < THREADS / 32; ++i) part += s_total[i];
+    } else {
+      __syncwarp();
     }
+    // every thread has read its c4 entries: re-zero for the next item (its first update is behind the final sync)
+    for (int i = tid; i < 256; i += THREADS) c4[i] = 0;
     const uint32_t total = part;
-
     if (slot == 0) {
-      for (int col = tid; col < (int)freq_stride; col += THREADS) {
-        uint32_t n = 0;
-        if (col < DBB_NUM_KMERS) {
-          n = c4[c_col_code1[col]];
-          const int c2 = c_col_code2[col];
-          if (c2 >= 0) n += c4[c2];
-          if (counts) counts[(size_t)item.scaffold * DBB_NUM_KMERS + col] = n;
-        }
-        if (freq)
-          freq[(size_t)item.scaffold * freq_stride + col] =
-              col < DBB_NUM_KMERS ? (float)((double)n / (double)total) : 0.f;
+      const double inv = 1.0 / (double)total;
+      #pragma unroll
+      for (int q = 0; q < NCOLT; ++q) {
+        const int col = tid + q * THREADS;
+        if (col < DBB_NUM_KMERS && counts) counts[(size_t)item.scaffold * DBB_NUM_KMERS + col] = nloc[q];
+        if (freq && col < (int)freq_stride)
+          freq[(size_t)item.scaffold * freq_stride + col] = col < DBB_NUM_KMERS ? (float)((double)nloc[q] * inv) : 0.f;
       }
     } else {
-      for (int col = tid; col < DBB_NUM_KMERS; col += THREADS) {
-        uint32_t n = c4[c_col_code1[col]];
-        const int c2 = c_col_code2[col];
-        if (c2 >= 0) n += c4[c2];
-        if (n) atomicAdd(&split_counts[(size_t)(slot - 1) * DBB_NUM_KMERS + col], n);
+      #pragma unroll
+      for (int q = 0; q < NCOLT; ++q) {
+        const int col = tid + q * THREADS;
+        if (col < DBB_NUM_KMERS && nloc[q]) atomicAdd(&split_counts[(size_t)(slot - 1) * DBB_NUM_KMERS + col], nloc[q]);
       }
     }
-    group_sync<THREADS>();
-    for (int i = tid; i < 256; i += THREADS) c4[i] = 0;
     group_sync<THREADS>();
     it = it_n;
     item = item_n;
@@ -352,6 +367,7 @@ int upload_tables() {
   const dbb::KmerTable& t = dbb::kmer_table();
   DBB_CUDA_TRY(cudaMemcpyToSymbol(c_col_code1, t.col_code1, sizeof(t.col_code1)));
   DBB_CUDA_TRY(cudaMemcpyToSymbol(c_col_code2, t.col_code2, sizeof(t.col_code2)));
+  { const char* e = getenv("DBB_K1_DEBUG_SKIP_FLUSH"); int v = (e && *e == '1') ? 1 : 0; DBB_CUDA_TRY(cudaMemcpyToSymbol(c_debug_skip_flush, &v, sizeof(int))); }
   g_tables_uploaded = true;
   return DBB_OK;
 }
