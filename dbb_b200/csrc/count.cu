@@ -414,7 +414,7 @@ DBB_EXPORT int dbb_count_plan_create(const int64_t* h_blk_off, int64_t n_seq, db
   cudaDeviceGetAttribute(&plan->sm_count, cudaDevAttrMultiProcessorCount, dev);
 
   // class thresholds in blocks (64 bases); env overrides are for tuning runs only
-  const int64_t t1 = env_i64("DBB_K1_T1", 44);          // <= 2.8 kb  : S = 1, one warp per scaffold
+  const int64_t t1 = env_i64("DBB_K1_T1", 128);         // <= 8 kb    : S = 1, one warp per scaffold
   const int64_t t2 = env_i64("DBB_K1_T2", 512);         // <= 33 kb   : S = 2
   const int64_t t3 = env_i64("DBB_K1_T3", 4300);        // <= 275 kb  : S = 3
   const int64_t chunk = env_i64("DBB_K1_CHUNK", 16384); // S = 4 chunk: 1 Mb
@@ -517,8 +517,8 @@ DBB_EXPORT int dbb_tetra_count_dev(dbb_count_plan* plan, const void* d_codes, co
 #define DBB_LAUNCH(S_, T_) rc = launch_class<S_, T_>(plan, c, d_codes, d_valid, d_counts, d_freq, freq_stride, cs)
     switch (c) {
       case 3: if (thr4 >= 1024) DBB_LAUNCH(4, 1024); else DBB_LAUNCH(4, 512); break;
-      case 2: if (thr3 >= 512) DBB_LAUNCH(3, 512); else if (thr3 >= 256) DBB_LAUNCH(3, 256); else DBB_LAUNCH(3, 128); break;
-      case 1: if (thr2 >= 256) DBB_LAUNCH(2, 256); else if (thr2 >= 128) DBB_LAUNCH(2, 128); else DBB_LAUNCH(2, 64); break;
+      case 2: if (thr3 >= 512) DBB_LAUNCH(3, 512); else if (thr3 >= 256) DBB_LAUNCH(3, 256); else if (thr3 >= 128) DBB_LAUNCH(3, 128); else DBB_LAUNCH(3, 64); break;
+      case 1: if (thr2 >= 256) DBB_LAUNCH(2, 256); else if (thr2 >= 128) DBB_LAUNCH(2, 128); else if (thr2 >= 64) DBB_LAUNCH(2, 64); else DBB_LAUNCH(2, 32); break;
       default: DBB_LAUNCH(1, 32); break;
     }
 #undef DBB_LAUNCH
