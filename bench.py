@@ -95,11 +95,16 @@ class ClockSampler(object):
                 'power_w_max': max(power) if power else None, 'samples': len(sm), 'reasons': sorted(reasons)}
 
 
-def workload(world, scale):
+def workload(world, scale, name='C2'):
+    """C2 (default): weak scaling, every rank brings 50 000 scaffolds.  C4: strong scaling, 1 000 000 scaffolds
+    in total (BASELINE.json configs[3]) sharded over the ranks."""
     from dbb_b200 import synthetic
-    kw = dict(synthetic.CONFIGS['C2'])
-    kw['n_scaffolds'] = max(64, int(kw['n_scaffolds'] * scale)) * world
-    kw['n_genomes'] = max(4, int(kw['n_genomes'] * min(1.0, scale * world)))
+    kw = dict(synthetic.CONFIGS[name])
+    if name == 'C2':
+        kw['n_scaffolds'] = max(64, int(kw['n_scaffolds'] * scale)) * world
+        kw['n_genomes'] = max(4, int(kw['n_genomes'] * min(1.0, scale * world)))
+    else:
+        kw['n_scaffolds'] = max(64 * world, int(kw['n_scaffolds'] * scale))
     return synthetic.make_metagenome(**kw), kw
 
 
@@ -209,6 +214,11 @@ def run_reference(args):
 
 
 def workload_config(args, world):
+    if getattr(args, 'workload', 'C2') != 'C2':
+        return {'workload': '%s: %d scaffolds in total over %d GPU(s) (strong scaling), tetramer signatures + k=%d TD kNN + TD '
+                            'neighbourhood (per=%d)' % (args.workload, int(1000000 * args.scale), world, K_NN, TD_PER),
+                'k': K_NN, 'td_percentile': TD_PER, 'scale': args.scale,
+                'l2_policy': 'inputs larger than L2', 'parallelism': 'scaffolds LPT-sharded for counting, 1 all-gather (NCCL), row-block kNN'}
     return {'workload': 'C2 per GPU: %d scaffolds x %d GPU(s), 1-100 kb log-uniform (~1.07 Gbp per GPU), tetramer signatures + '
                         'k=%d TD kNN + TD neighbourhood (per=%d) over all %d scaffolds'
                         % (int(50000 * args.scale), world, K_NN, TD_PER, int(50000 * args.scale) * world),
@@ -247,7 +257,7 @@ def run_ours(args):
         return float(t.item())
 
     # ---------------- workload ----------------
-    meta, kw = workload(world, args.scale)
+    meta, kw = workload(world, args.scale, args.workload)
     parts = parallel.lpt_partition(meta.length, world)
     order, _ = parallel.gathered_order(parts)
     mine = parts[rank]
@@ -298,44 +308,48 @@ def run_ours(args):
     pairs_total = float(n_total) * float(n_total)
     launches_per_step = plan.launches + int(_lib.lib().dbb_pairs_launches(n_total, r1 - r0))
 
-    # ---------------- end-to-end through the host-buffer C ABI (H2D + D2H inside the timed region) --------
-    h_ascii = torch.empty(d_ascii.shape, dtype=torch.uint8, pin_memory=True)
-    h_ascii.copy_(d_ascii); torch.cuda.synchronize()
-    a_np = h_ascii.numpy()
-    h_counts = torch.empty((my_n, 136), dtype=torch.int32, pin_memory=True).numpy().view(np.uint32)
-    h_freq = torch.empty((my_n, 136), dtype=torch.float32, pin_memory=True).numpy()
-    L = _lib.lib()
-    from dbb_b200 import _pairs
-
-    def e2e_count():
-        _lib.check(L.dbb_tetra_signatures_host(_lib.ptr(a_np), _lib.ptr(seq_off), my_n, _lib.ptr(h_counts), _lib.ptr(h_freq)))
-
-    def e2e_pairs():
-        if world == 1:
-            return _pairs.run_pairs_host(h_freq, tables, k=K_NN, want_count=True)
-        # N > 1: the host-produced signatures are gathered through the device, then the row block runs
-        # with its results copied back to the host
-        f = torch.from_numpy(h_freq).to(dev, non_blocking=True)
-        sig_all = parallel.all_gather_rows(device.pad_signatures(f), shard_counts)
-        res = device.pairs(sig_all, dt, r0, r1, k=K_NN, want_count=True)
-        return {k_: v.cpu() for k_, v in res.items()}
-
-    e2e_steps = max(1, min(args.steps, 5))
-    e2e_count(); e2e_pairs()
-    torch.cuda.synchronize(); barrier()
-    t0 = time.perf_counter()
-    tc = 0.0
-    for _ in range(e2e_steps):
-        t1 = time.perf_counter()
-        e2e_count()
-        tc += time.perf_counter() - t1
-        e2e_pairs()
-    torch.cuda.synchronize(); barrier()
-    e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
-    e2e_count_s = max_over_ranks(tc / e2e_steps)
+    e2e_s = e2e_count_s = None
+    h2d = d2h = 0
     rows = r1 - r0
-    h2d = int(a_np.nbytes + seq_off.nbytes * 2 + (n_total * 136 * 4 + n_total * 8 if world == 1 else my_n * 136 * 4))
-    d2h = int(my_n * 136 * 8 + rows * (K_NN * 8 + 12))
+    if not args.no_e2e:
+        # ---------------- end-to-end through the host-buffer C ABI (H2D + D2H inside the timed region) --------
+        h_ascii = torch.empty(d_ascii.shape, dtype=torch.uint8, pin_memory=True)
+        h_ascii.copy_(d_ascii); torch.cuda.synchronize()
+        a_np = h_ascii.numpy()
+        h_counts = torch.empty((my_n, 136), dtype=torch.int32, pin_memory=True).numpy().view(np.uint32)
+        h_freq = torch.empty((my_n, 136), dtype=torch.float32, pin_memory=True).numpy()
+        L = _lib.lib()
+        from dbb_b200 import _pairs
+
+        def e2e_count():
+            _lib.check(L.dbb_tetra_signatures_host(_lib.ptr(a_np), _lib.ptr(seq_off), my_n, _lib.ptr(h_counts), _lib.ptr(h_freq)))
+
+        def e2e_pairs():
+            if world == 1:
+                return _pairs.run_pairs_host(h_freq, tables, k=K_NN, want_count=True)
+            # N > 1: the host-produced signatures are gathered through the device, then the row block runs
+            # with its results copied back to the host
+            f = torch.from_numpy(h_freq).to(dev, non_blocking=True)
+            sig_all = parallel.all_gather_rows(device.pad_signatures(f), shard_counts)
+            res = device.pairs(sig_all, dt, r0, r1, k=K_NN, want_count=True)
+            return {k_: v.cpu() for k_, v in res.items()}
+
+        e2e_steps = max(1, min(args.steps, 5))
+        e2e_count(); e2e_pairs()
+        torch.cuda.synchronize(); barrier()
+        t0 = time.perf_counter()
+        tc = 0.0
+        for _ in range(e2e_steps):
+            t1 = time.perf_counter()
+            e2e_count()
+            tc += time.perf_counter() - t1
+            e2e_pairs()
+        torch.cuda.synchronize(); barrier()
+        e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+        e2e_count_s = max_over_ranks(tc / e2e_steps)
+        rows = r1 - r0
+        h2d = int(a_np.nbytes + seq_off.nbytes * 2 + (n_total * 136 * 4 + n_total * 8 if world == 1 else my_n * 136 * 4))
+        d2h = int(my_n * 136 * 8 + rows * (K_NN * 8 + 12))
 
     # ---------------- parity spot check (untimed): sampled scaffolds / rows against the oracle ----------
     verified = None
@@ -346,9 +360,10 @@ def run_ours(args):
         hc = counts.cpu().numpy().astype(np.int64)
         ok = True
         for i in sample:
-            s = a_np[seq_off[i]:seq_off[i + 1]]
+            s = d_ascii[int(seq_off[i]):int(seq_off[i + 1])].cpu().numpy()
             ok &= bool(np.array_equal(hc[i], O.seq_counts_np(s)))
-        ok &= bool(np.array_equal(h_counts.astype(np.int64), hc))
+        if not args.no_e2e:
+            ok &= bool(np.array_equal(h_counts.astype(np.int64), hc))
         verified = ok
         if not ok:
             raise SystemExit('bench.py: parity spot check FAILED (counts differ from the oracle)')
@@ -373,7 +388,7 @@ def run_ours(args):
         'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_step,
         'stages_ms': {'signatures': ms_count, 'allgather': ms_gather, 'knn': ms_knn},
         'pipeline': {'gbp_per_s': total_bp / (ms_step * 1e-3) / 1e9, 'pairs_per_s': pairs_total / (ms_step * 1e-3)},
-        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u32 counts / f32 distances',
+        'higher_is_better': True, 'scaling': 'weak' if args.workload == 'C2' else 'strong', 'vs_baseline': None, 'dtype': 'u32 counts / f32 distances',
         'data': 'synthetic', 'config': workload_config(args, world),
         'roofline': {'kernel': 'count_kernel<S> (stage 1, all classes of one launch set)', 'bound': 'hbm', 'achieved': gbs,
                      'peak': hbm_peak, 'unit': 'GB/s', 'frac': gbs / hbm_peak, 'traffic': traffic.get('count_dram_bytes_per_step'),
@@ -382,7 +397,7 @@ def run_ours(args):
                            'peak': fp32_peak / 1e12, 'unit': 'T lane-op/s', 'frac': lane_ops / fp32_peak,
                            'traffic': traffic.get('pairs_dram_bytes_per_step'),
                            'peak_source': '%d SMs x 128 FP32 lanes x %.0f MHz (272 lane-ops per pair)' % (sm_count, sm_max_mhz)},
-        'e2e': {'value': total_bp / e2e_count_s / 1e9, 'unit': 'Gbp/s', 'value2': pairs_total / max(e2e_s - e2e_count_s, 1e-9),
+        'e2e': None if args.no_e2e else {'value': total_bp / e2e_count_s / 1e9, 'unit': 'Gbp/s', 'value2': pairs_total / max(e2e_s - e2e_count_s, 1e-9),
                 'unit2': 'scaffold-pairs/s', 'ms_per_step': e2e_s * 1e3, 'steps': e2e_steps,
                 'pipeline_gbp_per_s': total_bp / e2e_s / 1e9, 'pipeline_pairs_per_s': pairs_total / e2e_s,
                 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
@@ -413,6 +428,8 @@ def main():
     ap.add_argument('--scale', type=float, default=1.0, help='fraction of the C2 scaffold count (tests only; 1.0 = the named config)')
     ap.add_argument('--cpu-seconds', type=float, default=8.0, help='target wall time of each CPU-baseline leg')
     ap.add_argument('--no-cpu', action='store_true', help='skip the CPU baseline leg')
+    ap.add_argument('--no-e2e', action='store_true', help='skip the host-buffer end-to-end leg (large exploratory workloads)')
+    ap.add_argument('--workload', default='C2', choices=['C2', 'C4'], help='C2 = the benchmark of record (weak scaling); C4 = 1M scaffolds, strong scaling')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)
