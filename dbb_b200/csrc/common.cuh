@@ -21,6 +21,9 @@ struct KmerTable {
 };
 const KmerTable& kmer_table();
 
+// internal: rebuild a count plan in place (count.cu), used by the host-buffer entry points
+int count_plan_rebuild(dbb_count_plan* plan, const int64_t* h_blk_off, int64_t n_seq, cudaStream_t st);
+
 }  // namespace dbb
 
 #define DBB_CUDA_TRY(expr)                                                                     \

@@ -346,10 +346,14 @@ struct dbb_count_plan {
   uint32_t class_begin[4] = {0, 0, 0, 0};
   uint32_t class_count[4] = {0, 0, 0, 0};
   Item* d_items = nullptr;
-  uint32_t* d_counters = nullptr;       // [4] dynamic work counters
+  size_t cap_items = 0;
+  uint32_t* d_counters = nullptr;       // [4] (kept for the ABI's memset; the schedule is static)
   uint32_t n_split = 0;
+  size_t cap_split = 0;
   uint32_t* d_split_scaffold = nullptr;
   uint32_t* d_split_counts = nullptr;
+  std::vector<Item> h_items;            // host staging of the last build (source of the async upload)
+  std::vector<uint32_t> h_split;
   int sm_count = 0;
   int launches = 0;
   // the four class kernels run concurrently on their own streams so that the tail of one overlaps the others
@@ -399,37 +403,34 @@ int launch_class(const dbb_count_plan* plan, int cls, const void* d_codes, const
 
 }  // namespace
 
-DBB_EXPORT int dbb_count_plan_create(const int64_t* h_blk_off, int64_t n_seq, dbb_count_plan** out) {
-  DBB_REQUIRE(out != nullptr && n_seq >= 0 && (n_seq == 0 || h_blk_off != nullptr), "bad arguments");
+namespace dbb {
+
+// (Re)build the work list of `plan` for a new batch, reusing its device allocations, streams and events when
+// they are large enough.  The upload is enqueued on `st`.
+int count_plan_rebuild(dbb_count_plan* plan, const int64_t* h_blk_off, int64_t n_seq, cudaStream_t st) {
+  DBB_REQUIRE(plan != nullptr && n_seq >= 0 && (n_seq == 0 || h_blk_off != nullptr), "bad arguments");
   DBB_REQUIRE(n_seq < (1ll << 32) - 1, "too many scaffolds");
-  *out = nullptr;
-  int rc = upload_tables();
-  if (rc != DBB_OK) return rc;
-  dbb_count_plan* plan = new dbb_count_plan();
   plan->n_seq = n_seq;
   plan->total_blocks = n_seq ? h_blk_off[n_seq] : 0;
-  if (plan->total_blocks >= (1ll << 32)) { delete plan; dbb::set_error("batch exceeds 2^32 blocks"); return DBB_ERR_INVALID; }
-  int dev = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&plan->sm_count, cudaDevAttrMultiProcessorCount, dev);
+  if (plan->total_blocks >= (1ll << 32)) { dbb::set_error("batch exceeds 2^32 blocks"); return DBB_ERR_INVALID; }
 
   // class thresholds in blocks (64 bases); env overrides are for tuning runs only
-  const int64_t t1 = env_i64("DBB_K1_T1", 128);         // <= 8 kb    : S = 1, one warp per scaffold
-  const int64_t t2 = env_i64("DBB_K1_T2", 512);         // <= 33 kb   : S = 2
-  const int64_t t3 = env_i64("DBB_K1_T3", 4300);        // <= 275 kb  : S = 3
-  const int64_t chunk = env_i64("DBB_K1_CHUNK", 16384); // S = 4 chunk: 1 Mb
+  static const int64_t t1 = env_i64("DBB_K1_T1", 128);         // <= 8 kb    : S = 1, one warp per scaffold
+  static const int64_t t2 = env_i64("DBB_K1_T2", 512);         // <= 33 kb   : S = 2
+  static const int64_t t3 = env_i64("DBB_K1_T3", 4300);        // <= 275 kb  : S = 3
+  static const int64_t chunk = env_i64("DBB_K1_CHUNK", 16384); // S = 4 chunk: 1 Mb
   std::vector<Item> cls[4];
-  std::vector<uint32_t> split_scaffold;
+  plan->h_split.clear();
   for (int64_t s = 0; s < n_seq; ++s) {
     const int64_t b0 = h_blk_off[s], nb = h_blk_off[s + 1] - b0;
-    if (nb < 0) { delete plan; dbb::set_error("block offsets must be non-decreasing"); return DBB_ERR_INVALID; }
+    if (nb < 0) { dbb::set_error("block offsets must be non-decreasing"); return DBB_ERR_INVALID; }
     if (nb <= chunk) {
       int c = nb <= t1 ? 0 : nb <= t2 ? 1 : nb <= t3 ? 2 : 3;
       cls[c].push_back(Item{(uint32_t)b0, (uint32_t)nb, (uint32_t)s, ITEM_LAST});
     } else {
-      const uint32_t slot = (uint32_t)split_scaffold.size() + 1;
-      if (slot >= ITEM_SLOT_MASK) { delete plan; dbb::set_error("too many split scaffolds"); return DBB_ERR_INVALID; }
-      split_scaffold.push_back((uint32_t)s);
+      const uint32_t slot = (uint32_t)plan->h_split.size() + 1;
+      if (slot >= ITEM_SLOT_MASK) { dbb::set_error("too many split scaffolds"); return DBB_ERR_INVALID; }
+      plan->h_split.push_back((uint32_t)s);
       for (int64_t o = 0; o < nb; o += chunk) {
         const int64_t len = std::min(chunk, nb - o);
         uint32_t flags = slot | (uint32_t)((o % 3) << 29) | (o + len == nb ? ITEM_LAST : 0u);
@@ -437,40 +438,70 @@ DBB_EXPORT int dbb_count_plan_create(const int64_t* h_blk_off, int64_t n_seq, db
       }
     }
   }
-  std::vector<Item> all;
-  all.reserve((size_t)n_seq + 16);
+  plan->h_items.clear();
+  plan->h_items.reserve((size_t)n_seq + 16);
   for (int c = 0; c < 4; ++c) {
     std::stable_sort(cls[c].begin(), cls[c].end(), [](const Item& a, const Item& b) { return a.n_blocks > b.n_blocks; });
-    plan->class_begin[c] = (uint32_t)all.size();
+    plan->class_begin[c] = (uint32_t)plan->h_items.size();
     plan->class_count[c] = (uint32_t)cls[c].size();
-    all.insert(all.end(), cls[c].begin(), cls[c].end());
+    plan->h_items.insert(plan->h_items.end(), cls[c].begin(), cls[c].end());
   }
-  plan->n_split = (uint32_t)split_scaffold.size();
+  plan->n_split = (uint32_t)plan->h_split.size();
   plan->launches = 0;
   for (int c = 0; c < 4; ++c) plan->launches += plan->class_count[c] ? 1 : 0;
   if (plan->n_split) plan->launches += 1;
 
   cudaError_t e = cudaSuccess;
-  if (!all.empty()) {
-    e = cudaMalloc(&plan->d_items, all.size() * sizeof(Item));
-    if (e == cudaSuccess) e = cudaMemcpy(plan->d_items, all.data(), all.size() * sizeof(Item), cudaMemcpyHostToDevice);
+  if (plan->h_items.size() > plan->cap_items) {
+    cudaFree(plan->d_items); plan->d_items = nullptr;
+    plan->cap_items = plan->h_items.size() + plan->h_items.size() / 4 + 64;
+    e = cudaMalloc(&plan->d_items, plan->cap_items * sizeof(Item));
+    if (e != cudaSuccess) plan->cap_items = 0;
   }
-  if (e == cudaSuccess) e = cudaMalloc(&plan->d_counters, 4 * sizeof(uint32_t));
+  if (e == cudaSuccess && !plan->h_items.empty())
+    e = cudaMemcpyAsync(plan->d_items, plan->h_items.data(), plan->h_items.size() * sizeof(Item), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && plan->n_split > plan->cap_split) {
+    cudaFree(plan->d_split_scaffold); cudaFree(plan->d_split_counts);
+    plan->d_split_scaffold = nullptr; plan->d_split_counts = nullptr;
+    plan->cap_split = (size_t)plan->n_split + 16;
+    e = cudaMalloc(&plan->d_split_scaffold, plan->cap_split * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&plan->d_split_counts, plan->cap_split * DBB_NUM_KMERS * sizeof(uint32_t));
+    if (e != cudaSuccess) plan->cap_split = 0;
+  }
+  if (e == cudaSuccess && plan->n_split)
+    e = cudaMemcpyAsync(plan->d_split_scaffold, plan->h_split.data(), plan->n_split * sizeof(uint32_t), cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) {
+    dbb::set_error("count plan allocation/upload failed: %s", cudaGetErrorString(e));
+    return e == cudaErrorMemoryAllocation ? DBB_ERR_NOMEM : DBB_ERR_CUDA;
+  }
+  return DBB_OK;
+}
+
+}  // namespace dbb
+
+DBB_EXPORT int dbb_count_plan_create(const int64_t* h_blk_off, int64_t n_seq, dbb_count_plan** out) {
+  DBB_REQUIRE(out != nullptr, "bad arguments");
+  *out = nullptr;
+  int rc = upload_tables();
+  if (rc != DBB_OK) return rc;
+  dbb_count_plan* plan = new dbb_count_plan();
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&plan->sm_count, cudaDevAttrMultiProcessorCount, dev);
+  cudaError_t e = cudaMalloc(&plan->d_counters, 4 * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&plan->ev_fork, cudaEventDisableTiming);
   for (int c = 0; c < 4 && e == cudaSuccess; ++c) {
     e = cudaStreamCreateWithFlags(&plan->class_stream[c], cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&plan->ev_join[c], cudaEventDisableTiming);
   }
-  if (e == cudaSuccess && plan->n_split) {
-    e = cudaMalloc(&plan->d_split_scaffold, plan->n_split * sizeof(uint32_t));
-    if (e == cudaSuccess) e = cudaMemcpy(plan->d_split_scaffold, split_scaffold.data(), plan->n_split * sizeof(uint32_t), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMalloc(&plan->d_split_counts, (size_t)plan->n_split * DBB_NUM_KMERS * sizeof(uint32_t));
-  }
   if (e != cudaSuccess) {
-    dbb::set_error("count plan allocation failed: %s", cudaGetErrorString(e));
+    dbb::set_error("count plan setup failed: %s", cudaGetErrorString(e));
     dbb_count_plan_destroy(plan);
-    return e == cudaErrorMemoryAllocation ? DBB_ERR_NOMEM : DBB_ERR_CUDA;
+    return DBB_ERR_CUDA;
   }
+  rc = dbb::count_plan_rebuild(plan, h_blk_off, n_seq, nullptr);
+  if (rc == DBB_OK && cudaStreamSynchronize(nullptr) != cudaSuccess) { dbb::set_error("count plan upload failed"); rc = DBB_ERR_CUDA; }
+  if (rc != DBB_OK) { dbb_count_plan_destroy(plan); return rc; }
   *out = plan;
   return DBB_OK;
 }

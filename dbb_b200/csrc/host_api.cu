@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include <algorithm>
 #include <cstdlib>
+#include <mutex>
 #include <vector>
 
 namespace {
@@ -56,8 +57,8 @@ int submit_batch(Lane& L, const uint8_t* ascii, const int64_t* seq_off, int64_t 
   DBB_TRY(L.valid.reserve((size_t)std::max<int64_t>(nblk, 1) * 8 + 16));
   if (want_counts) DBB_TRY(L.counts.reserve((size_t)ns * DBB_NUM_KMERS * 4));
   if (want_freq) DBB_TRY(L.freq.reserve((size_t)ns * DBB_NUM_KMERS * 4));
-  if (L.plan) { dbb_count_plan_destroy(L.plan); L.plan = nullptr; }
-  DBB_TRY(dbb_count_plan_create(L.h_blk.data(), ns, &L.plan));
+  if (!L.plan) DBB_TRY(dbb_count_plan_create(L.h_blk.data(), ns, &L.plan));
+  else DBB_TRY(dbb::count_plan_rebuild(L.plan, L.h_blk.data(), ns, L.st));
   if (nbytes) DBB_CUDA_TRY(cudaMemcpyAsync(L.ascii.p, ascii + byte0, nbytes, cudaMemcpyHostToDevice, L.st));
   DBB_CUDA_TRY(cudaMemcpyAsync(L.seq_off.p, L.h_off.data(), (ns + 1) * 8, cudaMemcpyHostToDevice, L.st));
   DBB_CUDA_TRY(cudaMemcpyAsync(L.blk_off.p, L.h_blk.data(), (ns + 1) * 8, cudaMemcpyHostToDevice, L.st));
@@ -86,14 +87,19 @@ DBB_EXPORT int dbb_tetra_signatures_host(const uint8_t* ascii, const int64_t* se
   DBB_REQUIRE(ascii != nullptr || seq_off[n_seq] == seq_off[0], "ascii is NULL");
   for (int64_t s = 0; s < n_seq; ++s) DBB_REQUIRE(seq_off[s + 1] >= seq_off[s], "seq_off must be non-decreasing");
 
-  // batches of ~batch_bytes of sequence, two in flight (copy of batch b+1 overlaps compute of batch b)
+  // batches of ~batch_bytes of sequence, two in flight (copy of batch b+1 overlaps compute of batch b).  The
+  // lanes (streams, device buffers, count plans) live for the whole process and only grow: a per-sequence caller
+  // such as GenomicSignatures.seqSignature pays no allocation after its first call.
+  static std::mutex mu;
+  static Lane lanes[2];
+  std::lock_guard<std::mutex> lock(mu);
   const char* env = getenv("DBB_HOST_BATCH_MB");
   const int64_t batch_bytes = (env && *env ? atoll(env) : 256) << 20;
-  Lane lanes[2];
   int rc = DBB_OK;
   for (auto& L : lanes) {
+    if (L.st) continue;
     cudaError_t e = cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking);
-    if (e != cudaSuccess) { dbb::set_error("cudaStreamCreate failed: %s", cudaGetErrorString(e)); rc = DBB_ERR_CUDA; }
+    if (e != cudaSuccess) { dbb::set_error("cudaStreamCreate failed: %s", cudaGetErrorString(e)); L.st = nullptr; return DBB_ERR_CUDA; }
   }
   int64_t s = 0;
   int cur = 0;
@@ -112,11 +118,10 @@ DBB_EXPORT int dbb_tetra_signatures_host(const uint8_t* ascii, const int64_t* se
   }
   for (int i = 0; i < 2; ++i) {
     Lane& L = lanes[cur ^ i];
-    if (rc == DBB_OK && pending[cur ^ i]) rc = collect_batch(L, counts, freq);
-  }
-  for (auto& L : lanes) {
-    if (L.st) { cudaStreamSynchronize(L.st); cudaStreamDestroy(L.st); }
-    if (L.plan) dbb_count_plan_destroy(L.plan);
+    if (pending[cur ^ i]) {
+      if (rc == DBB_OK) rc = collect_batch(L, counts, freq);
+      else cudaStreamSynchronize(L.st);
+    }
   }
   return rc;
 }
@@ -139,10 +144,13 @@ DBB_EXPORT int dbb_pairs_host(const dbb_pairs_input* in, int64_t row0, int64_t r
   if (row1 == row0 || in->n == 0) return DBB_OK;
   DBB_REQUIRE(in->sig && in->length, "sig/length are required");
   const size_t n = (size_t)in->n, rows = (size_t)(row1 - row0);
-  cudaStream_t st;
-  DBB_CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-  DevBuf dense, sig, len, tdb, gc, gcm, gcl, gclo, gchi, cov, covl, covlo, covhi;
-  DevBuf o_idx, o_dist, o_cnt, o_bp, o_td, o_gc, o_cov;
+  // process-lifetime scratch (grow-only), one host-buffer call at a time
+  static std::mutex mu;
+  static cudaStream_t st = nullptr;
+  static DevBuf dense, sig, len, tdb, gc, gcm, gcl, gclo, gchi, cov, covl, covlo, covhi;
+  static DevBuf o_idx, o_dist, o_cnt, o_bp, o_td, o_gc, o_cov;
+  std::lock_guard<std::mutex> lock(mu);
+  if (!st) DBB_CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   int rc = DBB_OK;
   dbb_pairs_input d = *in;
   dbb_pairs_output o = *out;
@@ -199,6 +207,5 @@ DBB_EXPORT int dbb_pairs_host(const dbb_pairs_input* in, int64_t row0, int64_t r
     if (e != cudaSuccess) { dbb::set_error("pairs_host failed: %s", cudaGetErrorString(e)); rc = DBB_ERR_CUDA; }
   } while (0);
   cudaStreamSynchronize(st);
-  cudaStreamDestroy(st);
   return rc;
 }
