@@ -35,6 +35,17 @@ class PairsOutput(ctypes.Structure):
                 ('td_mask', c_vp), ('gc_mask', c_vp), ('cov_mask', c_vp), ('mask_words', c_i64)]
 
 
+class RefineInput(ctypes.Structure):
+    _fields_ = [('n_unbinned', c_i64), ('n_cores', c_i64), ('u_sig', c_vp), ('c_sig', c_vp), ('u_gc', c_vp), ('u_cov', c_vp),
+                ('c_gc', c_vp), ('c_cov', c_vp), ('u_td_bound', c_vp), ('u_gc_lbin', c_vp), ('u_cov_lbin', c_vp),
+                ('c_gc_mbin', c_vp), ('gc_lo', c_vp), ('gc_hi', c_vp), ('gc_nm', c_i32), ('gc_nl', c_i32),
+                ('cov_lo', c_vp), ('cov_hi', c_vp), ('cov_nl', c_i32)]
+
+
+class RefineOutput(ctypes.Structure):
+    _fields_ = [('closest', c_vp), ('min_dist', c_vp), ('assigned', c_vp), ('within', c_vp)]
+
+
 # name -> (restype, argtypes); this table is also what tests/test_abi.py checks against the header
 SIGNATURES = {
     'dbb_last_error': (ctypes.c_char_p, []),
@@ -54,6 +65,8 @@ SIGNATURES = {
     'dbb_pairs_scratch_bytes': (c_i64, [c_i64, c_i64, c_i32]),
     'dbb_pairs_launches': (ctypes.c_int, [c_i64, c_i64]),
     'dbb_pairs_host': (ctypes.c_int, [ctypes.POINTER(PairsInput), c_i64, c_i64, ctypes.POINTER(PairsOutput)]),
+    'dbb_refine_dev': (ctypes.c_int, [ctypes.POINTER(RefineInput), ctypes.POINTER(RefineOutput), c_vp]),
+    'dbb_refine_host': (ctypes.c_int, [ctypes.POINTER(RefineInput), ctypes.POINTER(RefineOutput)]),
     'dbb_pad_signatures_dev': (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp]),
     'dbb_synth_ascii_dev': (ctypes.c_int, [ctypes.c_uint64, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp,
                                            c_vp, c_vp, c_vp]),

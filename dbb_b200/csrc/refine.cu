@@ -1,0 +1,172 @@
+// "Next" row N1: rectangular filtered nearest-core search.
+//
+// Reference semantics (refineBins.py:42-96, the same loop in unbinned.py:156-176): for every unbinned contig u,
+// over all core bins c in iteration order,
+//   valid(u,c) = withinDistGC(u,c) and withinDistCov(u,c) and L1(u.sig, c.sig) < boundDistTD(u)
+//     (distributions.py:75-127 with fixedSeqLen=None: GC bounds by (core mean-GC key, length key of u), coverage
+//      and TD bounds by the length key of u; core.coverage <= 0 -> 0.1)
+//   among the valid cores: closest in GC (|u.GC - c.GC|), in TD (the L1 distance) and in coverage
+//   (|u.cov - c.cov|) space, strict '<' so the first core in iteration order wins ties;
+//   u is assigned iff the three closest cores are the same one.
+// Everything is FP64, as in the reference (signatures are float64 there); the problem is U x B with B << N, so
+// FP64 throughput is ample (one warp per unbinned contig, cores streamed from L2).
+#include "common.cuh"
+#include <algorithm>
+
+namespace {
+
+struct RefineParams {
+  dbb_refine_input in;
+  dbb_refine_output out;
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+  #pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  return v;
+}
+
+__global__ void __launch_bounds__(256) refine_kernel(const RefineParams P) {
+  const int lane = threadIdx.x & 31;
+  const int64_t u = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const dbb_refine_input& I = P.in;
+  if (u >= I.n_unbinned) return;
+  const int64_t B = I.n_cores;
+  // the contig's signature: lane holds dimensions lane, lane+32, ...
+  double us[5];
+  #pragma unroll
+  for (int q = 0; q < 5; ++q) {
+    const int k = lane + 32 * q;
+    us[q] = k < DBB_NUM_KMERS ? I.u_sig[u * DBB_NUM_KMERS + k] : 0.0;
+  }
+  const double ugc = I.u_gc[u], ucov = I.u_cov[u], tdb = I.u_td_bound[u];
+  const int gcl = I.u_gc_lbin[u], covl = I.u_cov_lbin[u];
+  const double cov_lo = I.cov_lo[covl], cov_hi = I.cov_hi[covl];
+  int best[3] = {-1, -1, -1};
+  double bestd[3] = {1e9, 1e9, 1e9};                     // refineBins.py:56
+
+  for (int64_t c0 = 0; c0 < B; c0 += 32) {
+    // lanes evaluate the scalar predicates of 32 cores at once
+    const int64_t c = c0 + lane;
+    bool p_gc = false, p_cov = false;
+    double cgc = 0.0, ccov = 0.0;
+    if (c < B) {
+      cgc = I.c_gc[c]; ccov = I.c_cov[c];
+      const int m = I.c_gc_mbin[c];
+      const double lo = I.gc_lo[m * I.gc_nl + gcl], hi = I.gc_hi[m * I.gc_nl + gcl];
+      const double gdiff = ugc - cgc;
+      p_gc = gdiff >= lo && gdiff <= hi;
+      const double eff = ccov > 0 ? ccov : 0.1;
+      const double cdiff = (ucov - eff) * 100.0 / eff;
+      p_cov = cdiff >= cov_lo && cdiff <= cov_hi;
+    }
+    const uint32_t m_gc = __ballot_sync(0xffffffffu, p_gc), m_cov = __ballot_sync(0xffffffffu, p_cov);
+    // the TD distance is needed for cores that passed both (or for all of them when the flag matrix is wanted)
+    uint32_t todo = P.out.within ? __ballot_sync(0xffffffffu, c < B) : (m_gc & m_cov);
+    uint32_t m_td = 0;
+    while (todo) {
+      const int j = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const double* cs = I.c_sig + (c0 + j) * DBB_NUM_KMERS;
+      double part = 0.0;
+      #pragma unroll
+      for (int q = 0; q < 5; ++q) {
+        const int k = lane + 32 * q;
+        if (k < DBB_NUM_KMERS) part += fabs(us[q] - cs[k]);
+      }
+      const double d = warp_sum(part);
+      const bool p_td = d < tdb;                         // distributions.py:103-104 (strict)
+      if (p_td) m_td |= 1u << j;
+      if (p_td && ((m_gc & m_cov) >> j & 1u)) {
+        const double dg = fabs(ugc - __shfl_sync(0xffffffffu, cgc, j));
+        const double dc = fabs(ucov - __shfl_sync(0xffffffffu, ccov, j));
+        const int ci = (int)(c0 + j);
+        if (dg < bestd[0]) { bestd[0] = dg; best[0] = ci; }
+        if (d < bestd[1]) { bestd[1] = d; best[1] = ci; }
+        if (dc < bestd[2]) { bestd[2] = dc; best[2] = ci; }
+      } else {
+        __shfl_sync(0xffffffffu, cgc, j); __shfl_sync(0xffffffffu, ccov, j);   // keep the warp converged
+      }
+    }
+    if (P.out.within && c < B)
+      P.out.within[u * B + c] = (uint8_t)((p_gc ? 1 : 0) | (p_cov ? 2 : 0) | ((m_td >> lane & 1u) ? 4 : 0));
+  }
+  if (lane == 0) {
+    if (P.out.closest) { P.out.closest[u * 3] = best[0]; P.out.closest[u * 3 + 1] = best[1]; P.out.closest[u * 3 + 2] = best[2]; }
+    if (P.out.min_dist) { P.out.min_dist[u * 3] = bestd[0]; P.out.min_dist[u * 3 + 1] = bestd[1]; P.out.min_dist[u * 3 + 2] = bestd[2]; }
+    if (P.out.assigned) P.out.assigned[u] = (best[0] >= 0 && best[0] == best[1] && best[0] == best[2]) ? best[0] : -1;
+  }
+}
+
+struct Buf {
+  void* p = nullptr;
+  ~Buf() { if (p) cudaFree(p); }
+  template <typename T> int up(const T* h, size_t n, cudaStream_t st) {
+    if (cudaMalloc(&p, std::max<size_t>(n * sizeof(T), 16)) != cudaSuccess) { dbb::set_error("cudaMalloc failed in dbb_refine_host"); return DBB_ERR_NOMEM; }
+    if (n && cudaMemcpyAsync(p, h, n * sizeof(T), cudaMemcpyHostToDevice, st) != cudaSuccess) { dbb::set_error("H2D copy failed in dbb_refine_host"); return DBB_ERR_CUDA; }
+    return DBB_OK;
+  }
+  int alloc(size_t bytes) {
+    if (cudaMalloc(&p, std::max<size_t>(bytes, 16)) != cudaSuccess) { dbb::set_error("cudaMalloc failed in dbb_refine_host"); return DBB_ERR_NOMEM; }
+    return DBB_OK;
+  }
+};
+
+int check_input(const dbb_refine_input* in, const dbb_refine_output* out) {
+  DBB_REQUIRE(in && out, "NULL argument struct");
+  DBB_REQUIRE(in->n_unbinned >= 0 && in->n_cores >= 0, "negative size");
+  if (in->n_unbinned == 0) return DBB_OK;
+  DBB_REQUIRE(in->u_sig && in->u_gc && in->u_cov && in->u_td_bound && in->u_gc_lbin && in->u_cov_lbin, "incomplete unbinned inputs");
+  DBB_REQUIRE(in->n_cores == 0 || (in->c_sig && in->c_gc && in->c_cov && in->c_gc_mbin), "incomplete core inputs");
+  DBB_REQUIRE(in->gc_lo && in->gc_hi && in->cov_lo && in->cov_hi && in->gc_nm > 0 && in->gc_nl > 0 && in->cov_nl > 0, "incomplete tables");
+  DBB_REQUIRE(out->closest || out->assigned || out->within || out->min_dist, "no output requested");
+  return DBB_OK;
+}
+
+}  // namespace
+
+DBB_EXPORT int dbb_refine_dev(const dbb_refine_input* in, const dbb_refine_output* out, void* stream) {
+  int rc = check_input(in, out);
+  if (rc != DBB_OK || in->n_unbinned == 0) return rc;
+  RefineParams P;
+  P.in = *in; P.out = *out;
+  const int64_t grid = (in->n_unbinned + 7) / 8;
+  DBB_REQUIRE(grid < (1ll << 31), "too many unbinned contigs for one launch");
+  refine_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(P);
+  DBB_CUDA_TRY(cudaGetLastError());
+  return DBB_OK;
+}
+
+DBB_EXPORT int dbb_refine_host(const dbb_refine_input* in, const dbb_refine_output* out) {
+  int rc = check_input(in, out);
+  if (rc != DBB_OK || in->n_unbinned == 0) return rc;
+  const size_t U = (size_t)in->n_unbinned, B = (size_t)in->n_cores;
+  cudaStream_t st;
+  DBB_CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  Buf usig, csig, ugc, ucov, cgc, ccov, utd, ugl, ucl, cgm, glo, ghi, clo, chi, o_cl, o_md, o_as, o_wi;
+  dbb_refine_input d = *in;
+  dbb_refine_output o = *out;
+  do {
+#define UP(buf, field, count) if ((rc = buf.up(in->field, count, st)) != DBB_OK) break; d.field = (decltype(d.field))buf.p;
+    UP(usig, u_sig, U * DBB_NUM_KMERS) UP(csig, c_sig, B * DBB_NUM_KMERS) UP(ugc, u_gc, U) UP(ucov, u_cov, U)
+    UP(cgc, c_gc, B) UP(ccov, c_cov, B) UP(utd, u_td_bound, U) UP(ugl, u_gc_lbin, U) UP(ucl, u_cov_lbin, U) UP(cgm, c_gc_mbin, B)
+    UP(glo, gc_lo, (size_t)in->gc_nm * in->gc_nl) UP(ghi, gc_hi, (size_t)in->gc_nm * in->gc_nl)
+    UP(clo, cov_lo, (size_t)in->cov_nl) UP(chi, cov_hi, (size_t)in->cov_nl)
+#undef UP
+    if (out->closest) { if ((rc = o_cl.alloc(U * 12)) != DBB_OK) break; o.closest = (int32_t*)o_cl.p; }
+    if (out->min_dist) { if ((rc = o_md.alloc(U * 24)) != DBB_OK) break; o.min_dist = (double*)o_md.p; }
+    if (out->assigned) { if ((rc = o_as.alloc(U * 4)) != DBB_OK) break; o.assigned = (int32_t*)o_as.p; }
+    if (out->within) { if ((rc = o_wi.alloc(U * std::max<size_t>(B, 1))) != DBB_OK) break; o.within = (uint8_t*)o_wi.p; }
+    if ((rc = dbb_refine_dev(&d, &o, st)) != DBB_OK) break;
+    cudaError_t e = cudaSuccess;
+    if (out->closest) e = cudaMemcpyAsync(out->closest, o.closest, U * 12, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && out->min_dist) e = cudaMemcpyAsync(out->min_dist, o.min_dist, U * 24, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && out->assigned) e = cudaMemcpyAsync(out->assigned, o.assigned, U * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && out->within && B) e = cudaMemcpyAsync(out->within, o.within, U * B, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { dbb::set_error("dbb_refine_host failed: %s", cudaGetErrorString(e)); rc = DBB_ERR_CUDA; }
+  } while (0);
+  cudaStreamSynchronize(st);
+  cudaStreamDestroy(st);
+  return rc;
+}

@@ -145,6 +145,36 @@ int dbb_pairs_launches(int64_t n, int64_t rows);
 int dbb_pairs_host(const dbb_pairs_input* in_host, int64_t row0, int64_t row1,
                    const dbb_pairs_output* out_host);
 
+/* ---- "next" row N1: rectangular filtered nearest-core search -- refineBins.py:42-96 (__workerThread), the same
+ * ---- loop in unbinned.py:156-176.  For every unbinned contig u over all cores c (in array order):
+ * valid(u,c) = withinDistGC(u,c) && withinDistCov(u,c) && L1(u,c) < boundDistTD(u) (distributions.py:75-127 with
+ * fixedSeqLen = None); closest valid core in GC / TD / coverage space with strict '<' (first core wins ties);
+ * assigned iff the three agree.  All FP64, as in the reference.  Bounds are resolved per contig / per core on the
+ * host: u_td_bound[u] = tdDist[nearest(len_u)][tdKey], u_gc_lbin / u_cov_lbin = nearest length key of u,
+ * c_gc_mbin = nearest mean-GC key of the core. */
+typedef struct {
+  int64_t n_unbinned, n_cores;
+  const double* u_sig;         /* [U][136] */
+  const double* c_sig;         /* [B][136] */
+  const double* u_gc;  const double* u_cov;   /* [U] */
+  const double* c_gc;  const double* c_cov;   /* [B] */
+  const double* u_td_bound;    /* [U] */
+  const int32_t* u_gc_lbin; const int32_t* u_cov_lbin;   /* [U] */
+  const int32_t* c_gc_mbin;    /* [B] */
+  const double* gc_lo; const double* gc_hi; int32_t gc_nm, gc_nl;
+  const double* cov_lo; const double* cov_hi; int32_t cov_nl;
+} dbb_refine_input;
+
+typedef struct {
+  int32_t* closest;            /* [U][3] closest valid core in GC, TD, coverage space; -1 if no core is valid; or NULL */
+  double* min_dist;            /* [U][3] the three minimum distances (1e9 if none); or NULL */
+  int32_t* assigned;           /* [U] the core if the three agree, else -1; or NULL */
+  uint8_t* within;             /* [U][B] bit0 GC, bit1 coverage, bit2 TD predicate (unbinned.py:137-152); or NULL */
+} dbb_refine_output;
+
+int dbb_refine_dev(const dbb_refine_input* in, const dbb_refine_output* out, void* stream);
+int dbb_refine_host(const dbb_refine_input* in_host, const dbb_refine_output* out_host);
+
 /* dense [n][136] -> padded [n][DBB_SIG_STRIDE] on device (used after the all-gather) */
 int dbb_pad_signatures_dev(const float* d_dense, int64_t n, float* d_padded, void* stream);
 

@@ -439,3 +439,60 @@ def knn_rows_np(sig, rows, k, allowed=None):
         idx[n, :order.size] = order
         dist[n, :order.size] = d[n][order]
     return idx, dist, d
+
+
+# ----------------------------------------------------------------------------------------------
+# "next" row N1 -- refineBins.py:42-96 (one unbinned contig against all cores) and :288-304
+# ----------------------------------------------------------------------------------------------
+
+class Core(object):
+    """greedy.py:147-157."""
+
+    def __init__(self, binId, length, GC, coverage, tetraSig):
+        self.binId, self.length, self.GC, self.coverage, self.tetraSig = binId, length, GC, coverage, tetraSig
+
+
+def core_statistics_literal(binnedContigs, numKmers=NUM_KMERS):
+    """refineBins.py:288-304 (running length-weighted means, list-of-floats signature as the reference keeps it)."""
+    cores = {}
+    for contig in binnedContigs:
+        if contig.binId not in cores:
+            cores[contig.binId] = Core(contig.binId, 0, 0, 0, [0] * numKmers)
+        core = cores[contig.binId]
+        core.length += contig.length
+        weight = float(contig.length) / core.length
+        core.GC = contig.GC * weight + core.GC * (1.0 - weight)
+        core.coverage = contig.coverage * weight + core.coverage * (1.0 - weight)
+        for i in range(0, len(core.tetraSig)):
+            core.tetraSig[i] = contig.tetraSig[i] * weight + core.tetraSig[i] * (1.0 - weight)
+    return cores
+
+
+def refine_worker_literal(unbinnedContig, cores, distributions):
+    """refineBins.py:52-94 for one contig; ``cores`` is iterated in ascending binId order.  Returns
+    (closestBin[3], minDistances[3], newBinNum, bAssigned, bFailedDistanceTest, bInvalidWithAllCores)."""
+    closestBin = [None] * 3
+    minDistances = [1e9] * 3
+    for binId in sorted(cores):
+        core = cores[binId]
+        if not distributions.withinDistGC(unbinnedContig, core):
+            continue
+        if not distributions.withinDistCov(unbinnedContig, core):
+            continue
+        tdDistance = distance(unbinnedContig.tetraSig, np.asarray(core.tetraSig))
+        if not distributions.witinDistTD(tdDistance, unbinnedContig):
+            continue
+        distances = [abs(unbinnedContig.GC - core.GC), tdDistance, abs(unbinnedContig.coverage - core.coverage)]
+        for i, d in enumerate(distances):
+            if d < minDistances[i]:
+                minDistances[i] = d
+                closestBin[i] = binId
+    bAssigned = bFailed = bInvalid = False
+    if closestBin[0] is not None:
+        if closestBin[0] == closestBin[1] and closestBin[0] == closestBin[2]:
+            bAssigned, newBinNum = True, cores[closestBin[0]].binId
+        else:
+            bFailed, newBinNum = True, -1
+    else:
+        bInvalid, newBinNum = True, -1
+    return closestBin, minDistances, newBinNum, bAssigned, bFailed, bInvalid

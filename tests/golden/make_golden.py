@@ -36,10 +36,27 @@ sys.path.insert(0, os.path.join(HERE, '..', '..'))
 string.maketrans = str.maketrans
 _stub = types.ModuleType('seqUtils')
 _stub.readFasta = lambda path: {}
+_stub.readSeqStats = lambda path: {}
 sys.modules['seqUtils'] = _stub
 _common = types.ModuleType('common')
 _common.checkFileExists = lambda path: None
 sys.modules.setdefault('common', _common)
+# greedy.py is py2-only syntax (print statements); refineBins.py only needs these names from it
+_greedy = types.ModuleType('greedy')
+
+
+class _Greedy(object):
+    UNBINNED = -1
+
+
+class _Core(object):                                   # greedy.py:147-157
+    def __init__(self, binId, length, GC, coverage, tetraSig):
+        self.binId, self.length, self.GC, self.coverage, self.tetraSig, self.contigs = binId, length, GC, coverage, tetraSig, None
+
+
+_greedy.Greedy, _greedy.Core = _Greedy, _Core
+_greedy.Contig = _greedy.reportBins = _greedy.readContigIdtoBinId = None
+sys.modules['greedy'] = _greedy
 sys.path.insert(0, REF)
 
 from genomicSignatures import GenomicSignatures      # noqa: E402  (reference source)
@@ -47,6 +64,7 @@ from tdNeighbours import TdNeighbours                # noqa: E402
 from gcNeighbours import GcNeighbours                # noqa: E402
 from coverageNeighbours import CoverageNeighbours    # noqa: E402
 from distributions import Distributions              # noqa: E402
+from refineBins import RefineBins                    # noqa: E402
 
 
 class KeyListDict(dict):
@@ -138,6 +156,44 @@ def main():
         neigh['gc_' + tag] = run_rows(GcNeighbours(fixed), '_GcNeighbours__workerThread', contigs, dG)
         neigh['cov_' + tag] = run_rows(CoverageNeighbours(fixed), '_CoverageNeighbours__workerThread', contigs, dC)
     dist = np.array([[gs.distance(a.tetraSig, b.tetraSig) for b in contigs] for a in contigs])
+    tetra_snapshot = np.array([c.tetraSig for c in contigs])       # (row 8 is NaN here; part 4 restores it)
+
+    # ---- 4. refineBins.py:42-96 (__workerThread) on the same contigs: 30 binned into 4 cores, 18 unbinned -------
+    class IterDict(KeyListDict):
+        def iteritems(self):
+            return iter(sorted(self.items()))
+
+    for c in contigs:
+        c.binId = -1
+    contigs[8].tetraSig = gs.seqSignature(seqs_ascii[8].tobytes().decode('ascii'))     # undo the NaN row for this part
+    binned = contigs[:30]
+    for n, c in enumerate(binned):
+        c.binId = int(meta.genome[n])
+    cores = IterDict()
+    for c in binned:                                    # refineBins.py:288-304, verbatim arithmetic
+        if c.binId not in cores:
+            cores[c.binId] = _Core(c.binId, 0, 0, 0, [0] * gs.numKmers())
+        core = cores[c.binId]
+        core.length += c.length
+        weight = float(c.length) / core.length
+        core.GC = c.GC * weight + core.GC * (1.0 - weight)
+        core.coverage = c.coverage * weight + core.coverage * (1.0 - weight)
+        for i in range(0, len(core.tetraSig)):
+            core.tetraSig[i] = c.tetraSig[i] * weight + core.tetraSig[i] * (1.0 - weight)
+    unbinned = contigs[30:]
+    dR = Distributions(wrap(gcDist), 99, wrap(tdDist), 99, wrap(covDist), 99)
+    qin = ListQueue(list(range(len(unbinned))) + [None])
+    qout = ListQueue()
+    getattr(RefineBins(), '_RefineBins__workerThread')(unbinned, cores, dR, gs, qin, qout)
+    refine_rows = np.array([[r[0], r[1], r[2], int(r[3]), int(r[4]), int(r[5])] for r in qout.items])
+    neigh['refine_rows'] = refine_rows
+    neigh['refine_core_ids'] = np.array(sorted(cores.keys()))
+    neigh['refine_core_len'] = np.array([cores[k].length for k in sorted(cores.keys())])
+    neigh['refine_core_gc'] = np.array([cores[k].GC for k in sorted(cores.keys())])
+    neigh['refine_core_cov'] = np.array([cores[k].coverage for k in sorted(cores.keys())])
+    neigh['refine_core_sig'] = np.array([cores[k].tetraSig for k in sorted(cores.keys())])
+    neigh['refine_bin_of_contig'] = np.array([c.binId for c in contigs])
+    neigh['refine_sig8'] = contigs[8].tetraSig
 
     # the reference's td_dist.txt re-encoded as arrays (exact float64 values) for dbb_b200/data
     lens = sorted(tdDist.keys())
@@ -154,7 +210,7 @@ def main():
     np.savez_compressed(
         os.path.join(HERE, 'ref_neighbours.npz'),
         length=np.array([c.length for c in contigs]), GC=np.array([c.GC for c in contigs]),
-        coverage=np.array([c.coverage for c in contigs]), tetraSig=np.array([c.tetraSig for c in contigs]),
+        coverage=np.array([c.coverage for c in contigs]), tetraSig=tetra_snapshot,
         distance=dist, **neigh)
     print('wrote golden vectors: %d KAT sequences, %d contigs' % (len(kat), len(contigs)))
 

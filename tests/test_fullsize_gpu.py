@@ -101,3 +101,42 @@ def test_c5_like_skewed_lengths_counting():
     for i in list(range(meta.n_scaffolds - 3, meta.n_scaffolds)) + [0, 1, 2, 777]:
         s = d_ascii[seq_off[i]:seq_off[i + 1]].cpu().numpy()
         assert np.array_equal(c[i], O.seq_counts_np(s)), i
+
+
+def test_c1_whole_config_against_oracle():
+    """BASELINE.json configs[0] (2 000 scaffolds, 1-50 kb): every scaffold's counts, the full TD / GC / coverage
+    masks through the drop-in classes' kernel path and k = 20 for every row, against the oracle."""
+    from dbb_b200 import _pairs, synthetic
+    from dbb_b200.data import load_td_dist
+    from dbb_b200.distributions import PairTables
+    from dbb_b200.genomicSignatures import GenomicSignatures
+    meta = synthetic.make_config('C1')
+    seqs = synthetic.generate_sequences(meta)
+    counts, freq = GenomicSignatures(4, 1).signatures(seqs)
+    for i, s in enumerate(seqs):
+        assert np.array_equal(counts[i].astype(np.int64), O.seq_counts_np(s)), i
+    lit = np.random.RandomState(3).choice(meta.n_scaffolds, 12, replace=False)
+    for i in lit:                                                   # the literal (authoritative) form on a sample
+        assert O.seq_counts_literal(seqs[i].tobytes().decode('ascii')) == counts[i].tolist()
+    n = meta.n_scaffolds
+    td, gcd, cvd = load_td_dist(), synthetic.synthetic_gc_dist(), synthetic.synthetic_cov_dist(seed=1)
+    sig64 = counts.astype(np.float64) / counts.sum(axis=1, keepdims=True)
+    tables = PairTables(meta.length, GC=meta.gc_obs, coverage=meta.coverage, tdDist=td, tdDistPer=80, gcDist=gcd,
+                        gcDistPer=80, covDist=cvd, covDistPer=80)
+    res = _pairs.run_pairs_host(sig64, tables, k=20, want_count=True, want_td_mask=True, want_gc_mask=True, want_cov_mask=True)
+    rows = list(range(n))
+    ot = O.DistTables(gcd, 80, td, 80, cvd, 80)
+    s32 = sig64.astype(np.float32).astype(np.float64)
+    d64 = O.l1_rows_np(s32, rows)
+    assert np.array_equal(util.unpack_mask(res['gc_mask'], n), O.gc_rows_np(meta.length, meta.gc_obs, rows, ot, None))
+    assert np.array_equal(util.unpack_mask(res['cov_mask'], n), O.cov_rows_np(meta.length, meta.coverage, rows, ot, None))
+    flips = util.check_mask_against_oracle(util.unpack_mask(res['td_mask'], n), O.td_rows_np(s32, meta.length, rows, ot, None),
+                                           d64, O.td_bound_rows_np(meta.length, rows, ot, None))
+    assert flips <= 4
+    util.check_topk(res['idx'], res['dist'].astype(np.float64), d64, rows, 20)
+    # literal per-pair loop of tdNeighbours.py:41-51 on two rows
+    cs = [O.Contig('c', int(meta.length[i]), float(meta.gc_obs[i]), float(meta.coverage[i]), s32[i]) for i in range(n)]
+    dT = O.Distributions(None, None, td, 80, None, None)
+    for i in (0, 1234):
+        lit_row = O.td_row_literal(cs[i], cs, dT, None)
+        assert np.array_equal(lit_row, O.td_rows_np(s32, meta.length, [i], ot, None)[0])

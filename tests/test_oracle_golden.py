@@ -95,3 +95,29 @@ def test_tsv_format_is_py2_str():
     assert O.format_sig_value(1.0) == '1.0' and O.format_sig_value(0.0) == '0.0'
     assert O.format_sig_value(float('nan')) == 'nan' and O.format_sig_value(1e-05) == '1e-05'
     assert O.tsv_header().startswith('Sequence Id\tAAAA\tAAAC') and O.tsv_header().count('\t') == 136
+
+
+def _refine_setup():
+    from dbb_b200 import synthetic
+    from dbb_b200.data import load_td_dist
+    nb = util.golden_npz('ref_neighbours.npz')
+    sig = nb['tetraSig'].copy()
+    sig[8] = nb['refine_sig8']
+    cs = [O.Contig('c%d' % i, int(nb['length'][i]), float(nb['GC'][i]), float(nb['coverage'][i]), sig[i]) for i in range(sig.shape[0])]
+    for c, b in zip(cs, nb['refine_bin_of_contig']):
+        c.binId = int(b)
+    return nb, cs, (load_td_dist(), synthetic.synthetic_gc_dist(), synthetic.synthetic_cov_dist(seed=7))
+
+
+def test_refine_worker_matches_reference():
+    """refineBins.py:42-96 and :288-304 against the rows the reference's own __workerThread produced."""
+    nb, cs, (td, gcd, cvd) = _refine_setup()
+    cores = O.core_statistics_literal(cs[:30])
+    assert sorted(cores) == nb['refine_core_ids'].tolist()
+    for n, k in enumerate(sorted(cores)):
+        assert cores[k].length == nb['refine_core_len'][n] and cores[k].GC == nb['refine_core_gc'][n]
+        assert cores[k].coverage == nb['refine_core_cov'][n] and np.array_equal(np.array(cores[k].tetraSig), nb['refine_core_sig'][n])
+    dist = O.Distributions(gcd, 99, td, 99, cvd, 99)
+    for row, c in zip(nb['refine_rows'], cs[30:]):
+        _, _, newBin, bA, bF, bI = O.refine_worker_literal(c, cores, dist)
+        assert [newBin, c.length, int(bA), int(bF), int(bI)] == row[1:].tolist()

@@ -146,3 +146,49 @@ def test_column_split_items_merge_to_identical_results(monkeypatch):
         split = _pairs.run_pairs_host(sig64, tables, **kw)
         for key in whole:
             assert np.array_equal(whole[key], split[key]), (seg, key)
+
+
+def test_refine_closest_cores_vs_reference_rows_and_oracle():
+    """N1: dbb_b200.refineBins against the reference's own __workerThread rows (golden) and, on a larger random
+    instance, against the oracle's literal loop."""
+    from tests.test_oracle_golden import _refine_setup
+    from dbb_b200.refineBins import RefineBins, coreStatistics
+    nb, cs, (td, gcd, cvd) = _refine_setup()
+    cores = coreStatistics(cs[:30])
+    for n, k in enumerate(sorted(cores)):
+        assert cores[k].length == nb['refine_core_len'][n] and cores[k].GC == nb['refine_core_gc'][n]
+        assert np.array_equal(cores[k].tetraSig, nb['refine_core_sig'][n])
+    unb = cs[30:]
+    rows = RefineBins().refine(unb, cores, gcd, 99, td, 99, cvd, 99)
+    got = np.array([[r[0], r[1], r[2], int(r[3]), int(r[4]), int(r[5])] for r in rows])
+    assert np.array_equal(got, nb['refine_rows'])
+    assert [c.binId for c in unb] == nb['refine_rows'][:, 1].tolist()
+    # larger instance: 3 000 unbinned x 57 cores, with the per-pair flag matrix
+    from dbb_b200 import synthetic
+    from dbb_b200.genomicSignatures import GenomicSignatures
+    meta = synthetic.make_metagenome(seed=31, n_scaffolds=3600, min_len=1000, max_len=20000, n_genomes=57)
+    counts, _ = GenomicSignatures(4, 1).signatures(synthetic.generate_sequences(meta), want_freq=False)
+    sig = counts / counts.sum(axis=1, keepdims=True)
+    allc = [O.Contig('c%d' % i, int(meta.length[i]), float(meta.gc_obs[i]), float(meta.coverage[i]), sig[i]) for i in range(3600)]
+    for i, c in enumerate(allc):
+        c.binId = int(meta.genome[i])
+    allc[5].coverage = 0.0
+    cores = coreStatistics(allc[:600])
+    ocores = O.core_statistics_literal(allc[:600])
+    unb = allc[600:]
+    closest, mind, assigned, within = RefineBins().closestCores(unb, cores, gcd, 99, td, 99, cvd, 99, want_within=True)
+    dist = O.Distributions(gcd, 99, td, 99, cvd, 99)
+    order = sorted(ocores)
+    n_assigned = 0
+    for i in list(range(0, 3000, 7)) + [2999]:
+        cb, md, newBin, bA, bF, bI = O.refine_worker_literal(unb[i], ocores, dist)
+        exp = [-1 if b is None else order.index(b) for b in cb]
+        assert closest[i].tolist() == exp, i
+        assert np.allclose(mind[i], md, rtol=0, atol=1e-12)
+        assert (assigned[i] >= 0) == bA and (not bA or order[assigned[i]] == newBin)
+        n_assigned += bA
+        for b, k in enumerate(order):
+            f = within[i, b]
+            assert bool(f & 1) == dist.withinDistGC(unb[i], ocores[k]) and bool(f & 2) == dist.withinDistCov(unb[i], ocores[k])
+            assert bool(f & 4) == dist.witinDistTD(O.distance(unb[i].tetraSig, np.asarray(ocores[k].tetraSig)), unb[i])
+    assert n_assigned > 100
