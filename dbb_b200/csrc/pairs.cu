@@ -82,6 +82,8 @@ struct SmemLayout {
   int32_t cnt[TILE];                     // neighbourhood size per row
   float thr[TILE];                       // current k-th best distance per row (+inf until k found)
   int32_t qn[COMPUTE_WARPS];             // queue fill per warp
+  float ctdb[COMPUTE_WARPS][TILE];       // per-warp copy of the current column tile's TD bounds and lengths:
+  int32_t clen[COMPUTE_WARPS][TILE];     //   requested before the FADD2 loop, so their latency hides behind it
   alignas(8) uint64_t full[NSTAGE];
   uint64_t empty[NSTAGE];
   uint64_t a_full;
@@ -256,9 +258,9 @@ __device__ __noinline__ void drain_queue(SmemLayout& sm, const Params& P, int wa
     bool p_td = col_ok, p_gc = col_ok, p_cov = col_ok;
     if (col_ok) {
       const RowScalars rs = sm.rows[lr];
-      len_j = __ldg(P.length + cj);
+      len_j = sm.clen[warp][code & 127u];
       const bool i_core = rs.len > len_j;
-      if (F_TD) p_td = d < (i_core ? __ldg(P.td_bound + cj) : rs.tdb);
+      if (F_TD) p_td = d < (i_core ? sm.ctdb[warp][code & 127u] : rs.tdb);
       if (has_gc) {
         const int m = i_core ? rs.gcm : __ldg(P.gc_mbin + cj), l = i_core ? __ldg(P.gc_lbin + cj) : rs.gcl;
         const double lo = __ldg(P.gc_lo + m * P.gc_nl + l), hi = __ldg(P.gc_hi + m * P.gc_nl + l);
@@ -285,6 +287,7 @@ __device__ __noinline__ void drain_queue(SmemLayout& sm, const Params& P, int wa
       if (P.topk_filter & 2) cand = cand && p_gc;
       if (P.topk_filter & 4) cand = cand && p_cov;
       uint32_t m = __ballot_sync(0xffffffffu, cand);
+      if (P.debug_skip_epilogue == 3) m = 0;
       while (m) {
         const int src = __ffs(m) - 1;
         m &= m - 1;
@@ -387,6 +390,11 @@ __global__ void __launch_bounds__(THREADS, 1) pairs_kernel(const __grid_constant
     __syncwarp();
     mbar_wait(&sm.a_full, items_done & 1);
 
+    const float* a_base = &sm.a[0][warp * 16 + ty][0];
+    float4 av[8];                          // A values of the upcoming k4 step (software pipeline, see below)
+    #pragma unroll
+    for (int i = 0; i < 8; ++i) av[i] = *reinterpret_cast<const float4*>(a_base + (2 * i) * KCH);
+
     uint32_t l = 0;                        // chunk index within the item
     for (int ct = ct0; ct < ct1; ++ct) {
       float2 acc[8][8];
@@ -394,6 +402,15 @@ __global__ void __launch_bounds__(THREADS, 1) pairs_kernel(const __grid_constant
       for (int i = 0; i < 8; ++i)
         #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = make_float2(0.f, 0.f);
+      // column scalars of this tile (4 columns per lane), consumed by the epilogue
+      float pre_tdb[4];
+      int32_t pre_len[4];
+      #pragma unroll
+      for (int qq = 0; qq < 4; ++qq) {
+        const int64_t cj = (int64_t)ct * TILE + lane + 32 * qq;
+        pre_tdb[qq] = (F_TD && cj < n) ? __ldg(P.td_bound + cj) : -INFINITY;
+        pre_len[qq] = cj < n ? __ldg(P.length + cj) : 0;
+      }
 
       #pragma unroll 1
       for (int kc = 0; kc < NKC; ++kc, ++q, ++l) {
@@ -403,22 +420,33 @@ __global__ void __launch_bounds__(THREADS, 1) pairs_kernel(const __grid_constant
           issue_b(qbase + ln, ct0 + (int)(ln / NKC), (int)(ln % NKC));
         }
         mbar_wait(&sm.full[st], (q / NSTAGE) & 1);
-        const float* ap = &sm.a[kc][warp * 16 + ty][0];
         const float* bq = &sm.b[st][tx][0];
-        // NOT unrolled: one k4 step is ~280 instructions (4.4 KB).  Unrolling all 7 steps of a chunk (31 KB) cost
-        // ~25 % in instruction-fetch stalls; unrolling by two was 3 % slower than this (profiles/r01_pairs_notes.md).
+        // The A values of the NEXT k4 step are requested as soon as the current ones have seen their last use
+        // (column j = 7): the A tile is resident for the whole sweep, so the prefetch simply runs on across K
+        // chunks and column tiles and the step never starts by waiting for eight LDS.128.
+        // Not unrolled: one k4 step is ~280 instructions (4.4 KB); unrolling all 7 steps of a chunk (31 KB) cost
+        // ~25 % in instruction-fetch stalls, unrolling by two was 3 % slower (profiles/r01_pairs_notes.md).
         #pragma unroll 1
-        for (int k4 = 0; k4 < KCH / 4; ++k4) {
-          float4 av[8];
-          #pragma unroll
-          for (int i = 0; i < 8; ++i) av[i] = *reinterpret_cast<const float4*>(ap + (2 * i) * KCH + k4 * 4);
+        for (int k4 = (P.debug_skip_epilogue == 4 && warp >= 4) ? KCH / 4 : 0; k4 < KCH / 4; ++k4) {
+          const int nkc = (k4 + 1 < KCH / 4) ? kc : (kc + 1 < NKC ? kc + 1 : 0);
+          const int nk4 = (k4 + 1 < KCH / 4) ? k4 + 1 : 0;
+          const float* an = a_base + nkc * (TILE * KCH) + nk4 * 4;
           #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 bv = *reinterpret_cast<const float4*>(bq + (16 * j) * KCH + k4 * 4);
+            // eight independent subtractions, then the eight dependent accumulations: keeps every dependent
+            // FADD2 pair >= 8 issue slots apart (a lone warp otherwise stalls on the 4-cycle FADD2 latency)
+            float2 dd[8];
+            #pragma unroll
+            for (int i = 0; i < 8; ++i) dd[i] = __fadd2_rn(make_float2(av[i].x, av[i].y), make_float2(-bv.x, -bv.y));
+            #pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i][j] = __fadd2_rn(acc[i][j], make_float2(fabsf(dd[i].x), fabsf(dd[i].y)));
+            #pragma unroll
+            for (int i = 0; i < 8; ++i) dd[i] = __fadd2_rn(make_float2(av[i].z, av[i].w), make_float2(-bv.z, -bv.w));
             #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              acc[i][j] = absdiff_acc(acc[i][j], make_float2(av[i].x, av[i].y), make_float2(bv.x, bv.y));
-              acc[i][j] = absdiff_acc(acc[i][j], make_float2(av[i].z, av[i].w), make_float2(bv.z, bv.w));
+              acc[i][j] = __fadd2_rn(acc[i][j], make_float2(fabsf(dd[i].x), fabsf(dd[i].y)));
+              if (j == 7) av[i] = *reinterpret_cast<const float4*>(an + (2 * i) * KCH);
             }
           }
         }
@@ -428,7 +456,10 @@ __global__ void __launch_bounds__(THREADS, 1) pairs_kernel(const __grid_constant
 
       // ---------------- epilogue of this column tile ----------------
       const int64_t col_base = (int64_t)ct * TILE;
-      if (P.debug_skip_epilogue) {
+      #pragma unroll
+      for (int qq = 0; qq < 4; ++qq) { sm.ctdb[warp][lane + 32 * qq] = pre_tdb[qq]; sm.clen[warp][lane + 32 * qq] = pre_len[qq]; }
+      __syncwarp();
+      if (P.debug_skip_epilogue == 1 || P.debug_skip_epilogue == 4) {
         float keep = 0.f;
         #pragma unroll
         for (int i = 0; i < 8; ++i)
@@ -456,8 +487,11 @@ __global__ void __launch_bounds__(THREADS, 1) pairs_kernel(const __grid_constant
         for (int j = 0; j < 8; ++j) {
           const int64_t cj = col_base + tx + 16 * j;
           col_ok[j] = cj < n;
-          tdb_c[j] = (F_TD && col_ok[j]) ? __ldg(P.td_bound + cj) : -INFINITY;
+          tdb_c[j] = sm.ctdb[warp][tx + 16 * j];
         }
+        float tdb_cmax = tdb_c[0];
+        #pragma unroll
+        for (int j = 1; j < 8; ++j) tdb_cmax = fmaxf(tdb_cmax, tdb_c[j]);
         if (lane == 0) sm.qn[warp] = 0;
         __syncwarp();
         #pragma unroll
@@ -481,21 +515,27 @@ __global__ void __launch_bounds__(THREADS, 1) pairs_kernel(const __grid_constant
             thr_i = tau;
           }
           const float u = fmaxf(F_TD ? sm.rows[lr].tdb : -INFINITY, thr_i);
-          uint32_t bits = 0;
+          // cheap row test first: the smallest of the lane's 8 distances against the largest of its 8 bounds
+          float dmin = INFINITY;
           #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float d = acc[i][j].x + acc[i][j].y;
             acc[i][j].x = d;
-            bits |= (d <= fmaxf(u, tdb_c[j])) ? (1u << j) : 0u;
+            dmin = fminf(dmin, d);
           }
-          if (bits) {
-            int slot = atomicAdd(&sm.qn[warp], __popc(bits));    // reserve queue slots (hits are rare)
+          if (dmin <= fmaxf(u, tdb_cmax)) {
+            uint32_t bits = 0;
             #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              if (bits & (1u << j)) {
-                sm.qd[warp][slot] = acc[i][j].x;
-                sm.qcode[warp][slot] = (uint32_t)((2 * i + ty) << 7) | (uint32_t)(tx + 16 * j);
-                ++slot;
+            for (int j = 0; j < 8; ++j) bits |= (acc[i][j].x <= fmaxf(u, tdb_c[j])) ? (1u << j) : 0u;
+            if (bits) {
+              int slot = atomicAdd(&sm.qn[warp], __popc(bits));    // reserve queue slots (hits are rare)
+              #pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                if (bits & (1u << j)) {
+                  sm.qd[warp][slot] = acc[i][j].x;
+                  sm.qcode[warp][slot] = (uint32_t)((2 * i + ty) << 7) | (uint32_t)(tx + 16 * j);
+                  ++slot;
+                }
               }
             }
           }
@@ -508,7 +548,7 @@ __global__ void __launch_bounds__(THREADS, 1) pairs_kernel(const __grid_constant
           }
         }
         const int qn = sm.qn[warp];
-        if (qn) drain_queue<FLAGS>(sm, P, warp, lane, qn, row_base, col_base);
+        if (qn && P.debug_skip_epilogue != 2) drain_queue<FLAGS>(sm, P, warp, lane, qn, row_base, col_base);
       }
     }  // column tiles
 
@@ -722,7 +762,7 @@ DBB_EXPORT int dbb_pairs_dev(const dbb_pairs_input* in, int64_t row0, int64_t ro
   P.n_full_rt = (int32_t)n_full;
   P.n_seg = n_seg;
   P.n_items = (int32_t)(n_full + rem * n_seg);
-  { const char* e2 = getenv("DBB_K2_DEBUG_SKIP_EPILOGUE"); P.debug_skip_epilogue = (e2 && *e2 == '1') ? 1 : 0; }   // profiling only
+  { const char* e2 = getenv("DBB_K2_DEBUG_SKIP_EPILOGUE"); P.debug_skip_epilogue = (e2 && *e2) ? atoi(e2) : 0; }   // profiling only
   const int64_t split_rows = std::min<int64_t>(rem * TILE, n_rows - n_full * TILE);
   const size_t k_ = (size_t)std::max(out->k, 1);
   size_t off_idx = 256, off_dist, off_cnt, off_bp, total;

@@ -23,3 +23,5 @@ def run(label, **env):
     print('%-40s %.3f ms  %.1f G pairs/s' % (label, ms, n * n / ms / 1e6), flush=True)
 run('default', DBB_K2_DEBUG_SKIP_EPILOGUE='0')
 run('skip epilogue', DBB_K2_DEBUG_SKIP_EPILOGUE='1')
+run('no epilogue, only warps 0-3 compute (4)', DBB_K2_DEBUG_SKIP_EPILOGUE='4')
+run('default again', DBB_K2_DEBUG_SKIP_EPILOGUE='0')

@@ -48,20 +48,20 @@ __global__ void __launch_bounds__(256, 1) k(int iters, float* out, unsigned long
 }
 
 template <int MIX>
-void run(int iters) {
+void run(int iters, int threads = 256) {
   int nsm; CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0));
   float* out; unsigned long long* cyc; CK(cudaMalloc(&out, (size_t)nsm * 256 * 4)); CK(cudaMalloc(&cyc, nsm * 8));
-  k<MIX><<<nsm, 256>>>(iters / 8 + 1, out, cyc, 0.001f); CK(cudaDeviceSynchronize());
-  k<MIX><<<nsm, 256>>>(iters, out, cyc, 0.001f); CK(cudaDeviceSynchronize());
+  k<MIX><<<nsm, threads>>>(iters / 8 + 1, out, cyc, 0.001f); CK(cudaDeviceSynchronize());
+  k<MIX><<<nsm, threads>>>(iters, out, cyc, 0.001f); CK(cudaDeviceSynchronize());
   unsigned long long* h = (unsigned long long*)malloc(nsm * 8);
   CK(cudaMemcpy(h, cyc, nsm * 8, cudaMemcpyDeviceToHost));
   unsigned long long mx = 0; for (int i = 0; i < nsm; ++i) if (h[i] > mx) mx = h[i];
-  double pairdims = (double)iters * 64 * 2 * 256;      // per SM
-  printf("min-form columns %d/8: %.1f pair-dims/clk/SM  (direct-only peak is 64)\n", MIX, pairdims / mx);
+  double pairdims = (double)iters * 64 * 2 * threads;      // per SM
+  printf("threads/SM %d, min-form columns %d/8: %.1f pair-dims/clk/SM  (direct-only peak is 64)\n", threads, MIX, pairdims / mx);
   cudaFree(out); cudaFree(cyc); free(h);
 }
 
 int main() {
-  run<0>(4000); run<2>(4000); run<4>(4000); run<5>(4000); run<6>(4000); run<8>(4000);
+  run<0>(4000, 128); run<0>(4000, 256); run<0>(4000, 512); run<2>(4000); run<4>(4000); run<5>(4000); run<6>(4000); run<8>(4000);
   return 0;
 }
