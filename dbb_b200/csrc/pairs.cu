@@ -39,11 +39,11 @@ constexpr int KCH = 28;                      // floats per K chunk
 constexpr int NKC = DBB_SIG_STRIDE / KCH;    // 5
 constexpr int NSTAGE = 4;
 constexpr int CHUNK_BYTES = TILE * KCH * 4;  // 14336
-constexpr int COMPUTE_WARPS = 8;
-constexpr int THREADS = COMPUTE_WARPS * 32;       // 8 warps: register allocation is per 4 warps
+constexpr int MAX_WARPS = 16;                // the kernel is instantiated for 8 warps (8x8 register tiles, <= 255
+                                             // registers) and 16 warps (4x8 tiles, <= 128 registers, 4 warps per sub-partition)
 constexpr int PREFETCH = 2;                  // B chunks in flight ahead of the consumers
 constexpr int LIST_K = DBB_MAX_K;            // list slots per row
-constexpr int QCAP = 512;                    // queue entries per warp (>= 2 x the 256 pushes of one row pair)
+constexpr int QTOTAL = 5120;                 // queue entries per CTA; per warp QTOTAL / WARPS (>= 256 + one row pair's pushes)
 
 struct RowScalars {       // staged in shared memory per row tile
   int32_t len;
@@ -74,16 +74,16 @@ struct SmemLayout {
   alignas(128) float b[NSTAGE][TILE][KCH];
   float list_d[TILE][LIST_K];
   int32_t list_j[TILE][LIST_K];
-  float qd[COMPUTE_WARPS][QCAP];         // per-warp queue of pairs that may be a neighbour or a top-k candidate
+  float qd[QTOTAL];                       // per-warp queue of pairs that may be a neighbour or a top-k candidate
                                          //   (the every-pair path reuses the first 256 entries as its scratch)
-  uint32_t qcode[COMPUTE_WARPS][QCAP];   //   (row within the warp's 16) << 7 | (column within the tile)
+  uint32_t qcode[QTOTAL];                //   (row within the warp's rows) << 7 | (column within the tile)
   RowScalars rows[TILE];
   uint32_t bp_lo[TILE], bp_hi[TILE];     // neighbourhood base pairs per row (64-bit as two native 32-bit atomics)
   int32_t cnt[TILE];                     // neighbourhood size per row
   float thr[TILE];                       // current k-th best distance per row (+inf until k found)
-  int32_t qn[COMPUTE_WARPS];             // queue fill per warp
-  float ctdb[COMPUTE_WARPS][TILE];       // per-warp copy of the current column tile's TD bounds and lengths:
-  int32_t clen[COMPUTE_WARPS][TILE];     //   requested before the FADD2 loop, so their latency hides behind it
+  int32_t qn[MAX_WARPS];                 // queue fill per warp
+  float ctdb[MAX_WARPS][TILE];           // per-warp copy of the current column tile's TD bounds and lengths:
+  int32_t clen[MAX_WARPS][TILE];         //   requested before the FADD2 loop, so their latency hides behind it
   alignas(8) uint64_t full[NSTAGE];
   uint64_t empty[NSTAGE];
   uint64_t a_full;
@@ -151,10 +151,11 @@ __device__ __forceinline__ float list_insert(SmemLayout& sm, int row, float d, i
 // Slow path of the epilogue (one call per row pair that may hold a neighbour or a top-k candidate):
 // evaluates the predicates of the 2 x 128 pairs whose distances sit in sm.scratch[warp], updates the
 // per-row counts / base pairs / masks / top-k lists.  Whole warp, lanes 0-15 -> row lr0, 16-31 -> lr0+1.
-template <int FLAGS>
+template <int FLAGS, int WARPS>
 __device__ __noinline__ void process_row_pair(SmemLayout& sm, const Params& P, int warp, int lane, int lr0,
                                               int64_t row_base, int64_t col_base) {
   constexpr bool F_TD = (FLAGS & 1) != 0, F_GCCOV = (FLAGS & 2) != 0, F_MASK = (FLAGS & 4) != 0, F_TOPK = (FLAGS & 8) != 0;
+  constexpr int QCAP = QTOTAL / WARPS;
   const int ty = lane >> 4, tx = lane & 15;
   const int lr = lr0 + ty;
   const int64_t gi = row_base + lr;
@@ -165,7 +166,7 @@ __device__ __noinline__ void process_row_pair(SmemLayout& sm, const Params& P, i
   const int k = P.k;
   #pragma unroll 1
   for (int j = 0; j < 8; ++j) {
-    const float d = sm.qd[warp][j * 32 + lane];
+    const float d = sm.qd[warp * QCAP + (j * 32 + lane)];
     const int64_t cj = col_base + tx + 16 * j;
     const bool col_ok = cj < n;
     int32_t len_j = 0;
@@ -236,10 +237,11 @@ __device__ __noinline__ void process_row_pair(SmemLayout& sm, const Params& P, i
 // Steady-state slow path: the warp's queue holds (distance, row, column) of the few pairs of this column
 // tile that passed the conservative in-register test.  Lane-parallel predicates and counts, then the
 // (rare) top-k candidates are inserted one at a time, warp-cooperatively.
-template <int FLAGS>
+template <int FLAGS, int WARPS>
 __device__ __noinline__ void drain_queue(SmemLayout& sm, const Params& P, int warp, int lane, int qn,
                                          int64_t row_base, int64_t col_base) {
   constexpr bool F_TD = (FLAGS & 1) != 0, F_GCCOV = (FLAGS & 2) != 0, F_TOPK = (FLAGS & 8) != 0;
+  constexpr int QCAP = QTOTAL / WARPS, RW = TILE / WARPS;
   const int64_t n = P.n;
   const bool has_gc = F_GCCOV && P.gc != nullptr, has_cov = F_GCCOV && P.cov != nullptr;
   const bool want_cnt = P.count != nullptr || P.neighbour_bp != nullptr;
@@ -248,9 +250,9 @@ __device__ __noinline__ void drain_queue(SmemLayout& sm, const Params& P, int wa
   for (int base = 0; base < qn; base += 32) {
     const int e = base + lane;
     const bool valid = e < qn;
-    const float d = valid ? sm.qd[warp][e] : INFINITY;
-    const uint32_t code = valid ? sm.qcode[warp][e] : 0u;
-    const int lr = warp * 16 + (int)(code >> 7);
+    const float d = valid ? sm.qd[warp * QCAP + (e)] : INFINITY;
+    const uint32_t code = valid ? sm.qcode[warp * QCAP + (e)] : 0u;
+    const int lr = warp * RW + (int)(code >> 7);
     const int64_t cj = col_base + (code & 127u);
     const int64_t gi = row_base + lr;
     const bool col_ok = valid && cj < n;
@@ -306,9 +308,12 @@ __device__ __noinline__ void drain_queue(SmemLayout& sm, const Params& P, int wa
 }
 
 // FLAGS: bit0 TD predicate, bit1 GC and/or coverage predicates, bit2 masks, bit3 top-k
-template <int FLAGS>
-__global__ void __launch_bounds__(THREADS, 1) pairs_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Params P) {
+template <int FLAGS, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) pairs_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Params P) {
   constexpr bool F_TD = (FLAGS & 1) != 0, F_GCCOV = (FLAGS & 2) != 0, F_MASK = (FLAGS & 4) != 0, F_TOPK = (FLAGS & 8) != 0;
+  constexpr int RW = TILE / WARPS;          // rows per warp: 16 or 8
+  constexpr int RI = RW / 2;                // rows per lane: 8 or 4 (lane owns rows warp*RW + 2i + ty)
+  constexpr int QCAP = QTOTAL / WARPS;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   SmemLayout& sm = *reinterpret_cast<SmemLayout*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -318,7 +323,7 @@ __global__ void __launch_bounds__(THREADS, 1) pairs_kernel(const __grid_constant
   const int n_ct = (int)((n + TILE - 1) / TILE);
 
   if (tid == 0) {
-    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], COMPUTE_WARPS); }
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], WARPS); }
     mbar_init(&sm.a_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -367,8 +372,8 @@ __global__ void __launch_bounds__(THREADS, 1) pairs_kernel(const __grid_constant
       for (uint32_t l = 0; l < (uint32_t)PREFETCH && l < item_chunks; ++l) issue_b(qbase + l, ct0 + (int)(l / NKC), (int)(l % NKC));
     }
     // stage row scalars and reset the per-row state of this warp's 16 rows
-    if (lane < 16) {
-      const int lr = warp * 16 + lane;
+    if (lane < RW) {
+      const int lr = warp * RW + lane;
       const int64_t gr = row_base + lr;
       RowScalars rs;
       rs.len = 0; rs.tdb = 0.f; rs.gcm = 0; rs.gcl = 0; rs.covl = 0; rs.pad = 0; rs.gc = 0.0; rs.cov = 0.0;
@@ -383,23 +388,23 @@ __global__ void __launch_bounds__(THREADS, 1) pairs_kernel(const __grid_constant
       sm.bp_lo[lr] = 0u; sm.bp_hi[lr] = 0u;
       sm.thr[lr] = F_TOPK ? INFINITY : -INFINITY;
     }
-    for (int r = 0; r < 16; ++r) {
-      sm.list_d[warp * 16 + r][lane] = INFINITY;
-      sm.list_j[warp * 16 + r][lane] = INT_MAX;
+    for (int r = 0; r < RW; ++r) {
+      sm.list_d[warp * RW + r][lane] = INFINITY;
+      sm.list_j[warp * RW + r][lane] = INT_MAX;
     }
     __syncwarp();
     mbar_wait(&sm.a_full, items_done & 1);
 
-    const float* a_base = &sm.a[0][warp * 16 + ty][0];
-    float4 av[8];                          // A values of the upcoming k4 step (software pipeline, see below)
+    const float* a_base = &sm.a[0][warp * RW + ty][0];
+    float4 av[RI];                         // A values of the upcoming k4 step (software pipeline, see below)
     #pragma unroll
-    for (int i = 0; i < 8; ++i) av[i] = *reinterpret_cast<const float4*>(a_base + (2 * i) * KCH);
+    for (int i = 0; i < RI; ++i) av[i] = *reinterpret_cast<const float4*>(a_base + (2 * i) * KCH);
 
     uint32_t l = 0;                        // chunk index within the item
     for (int ct = ct0; ct < ct1; ++ct) {
-      float2 acc[8][8];
+      float2 acc[RI][8];
       #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < RI; ++i)
         #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = make_float2(0.f, 0.f);
       // column scalars of this tile (4 columns per lane), consumed by the epilogue
@@ -436,15 +441,15 @@ __global__ void __launch_bounds__(THREADS, 1) pairs_kernel(const __grid_constant
             const float4 bv = *reinterpret_cast<const float4*>(bq + (16 * j) * KCH + k4 * 4);
             // eight independent subtractions, then the eight dependent accumulations: keeps every dependent
             // FADD2 pair >= 8 issue slots apart (a lone warp otherwise stalls on the 4-cycle FADD2 latency)
-            float2 dd[8];
+            float2 dd[RI];
             #pragma unroll
-            for (int i = 0; i < 8; ++i) dd[i] = __fadd2_rn(make_float2(av[i].x, av[i].y), make_float2(-bv.x, -bv.y));
+            for (int i = 0; i < RI; ++i) dd[i] = __fadd2_rn(make_float2(av[i].x, av[i].y), make_float2(-bv.x, -bv.y));
             #pragma unroll
-            for (int i = 0; i < 8; ++i) acc[i][j] = __fadd2_rn(acc[i][j], make_float2(fabsf(dd[i].x), fabsf(dd[i].y)));
+            for (int i = 0; i < RI; ++i) acc[i][j] = __fadd2_rn(acc[i][j], make_float2(fabsf(dd[i].x), fabsf(dd[i].y)));
             #pragma unroll
-            for (int i = 0; i < 8; ++i) dd[i] = __fadd2_rn(make_float2(av[i].z, av[i].w), make_float2(-bv.z, -bv.w));
+            for (int i = 0; i < RI; ++i) dd[i] = __fadd2_rn(make_float2(av[i].z, av[i].w), make_float2(-bv.z, -bv.w));
             #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < RI; ++i) {
               acc[i][j] = __fadd2_rn(acc[i][j], make_float2(fabsf(dd[i].x), fabsf(dd[i].y)));
               if (j == 7) av[i] = *reinterpret_cast<const float4*>(an + (2 * i) * KCH);
             }
@@ -462,18 +467,18 @@ __global__ void __launch_bounds__(THREADS, 1) pairs_kernel(const __grid_constant
       if (P.debug_skip_epilogue == 1 || P.debug_skip_epilogue == 4) {
         float keep = 0.f;
         #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < RI; ++i)
           #pragma unroll
           for (int j = 0; j < 8; ++j) keep += acc[i][j].x + acc[i][j].y;
         if (keep == -1.f) sm.thr[0] = keep;
       } else if (always_slow) {
         // every pair matters (masks, or counts without a TD bound): evaluate all of them
         #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < RI; ++i) {
           #pragma unroll
-          for (int j = 0; j < 8; ++j) sm.qd[warp][j * 32 + lane] = acc[i][j].x + acc[i][j].y;
+          for (int j = 0; j < 8; ++j) sm.qd[warp * QCAP + (j * 32 + lane)] = acc[i][j].x + acc[i][j].y;
           __syncwarp();
-          process_row_pair<FLAGS>(sm, P, warp, lane, warp * 16 + 2 * i, row_base, col_base);
+          process_row_pair<FLAGS, WARPS>(sm, P, warp, lane, warp * RW + 2 * i, row_base, col_base);
         }
       } else {
         // A pair is queued only if it can be a TD neighbour (d below the larger of the two bounds -- the exact
@@ -495,8 +500,8 @@ __global__ void __launch_bounds__(THREADS, 1) pairs_kernel(const __grid_constant
         if (lane == 0) sm.qn[warp] = 0;
         __syncwarp();
         #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int lr = warp * 16 + 2 * i + ty;
+        for (int i = 0; i < RI; ++i) {
+          const int lr = warp * RW + 2 * i + ty;
           float thr_i = F_TOPK ? sm.thr[lr] : -INFINITY;
           if (first_tile) {
             const int m = (P.k + 16) / 16;                       // 1, 2 or 3
@@ -532,8 +537,8 @@ __global__ void __launch_bounds__(THREADS, 1) pairs_kernel(const __grid_constant
               #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 if (bits & (1u << j)) {
-                  sm.qd[warp][slot] = acc[i][j].x;
-                  sm.qcode[warp][slot] = (uint32_t)((2 * i + ty) << 7) | (uint32_t)(tx + 16 * j);
+                  sm.qd[warp * QCAP + (slot)] = acc[i][j].x;
+                  sm.qcode[warp * QCAP + (slot)] = (uint32_t)((2 * i + ty) << 7) | (uint32_t)(tx + 16 * j);
                   ++slot;
                 }
               }
@@ -542,21 +547,21 @@ __global__ void __launch_bounds__(THREADS, 1) pairs_kernel(const __grid_constant
           __syncwarp();
           const int qn = sm.qn[warp];
           if (qn > QCAP - 256) {                                 // one row pair pushes at most 256 entries
-            drain_queue<FLAGS>(sm, P, warp, lane, qn, row_base, col_base);
+            drain_queue<FLAGS, WARPS>(sm, P, warp, lane, qn, row_base, col_base);
             if (lane == 0) sm.qn[warp] = 0;
             __syncwarp();
           }
         }
         const int qn = sm.qn[warp];
-        if (qn && P.debug_skip_epilogue != 2) drain_queue<FLAGS>(sm, P, warp, lane, qn, row_base, col_base);
+        if (qn && P.debug_skip_epilogue != 2) drain_queue<FLAGS, WARPS>(sm, P, warp, lane, qn, row_base, col_base);
       }
     }  // column tiles
 
     // ---------------- per-row outputs (final for whole sweeps, partial for column segments) -----------
     __syncwarp();
     const int k = P.k;
-    if (lane < 16) {
-      const int lr = warp * 16 + lane;
+    if (lane < RW) {
+      const int lr = warp * RW + lane;
       const int64_t gi = row_base + lr;
       if (gi < P.row1) {
         const int64_t bp = (int64_t)(((unsigned long long)sm.bp_hi[lr] << 32) | sm.bp_lo[lr]);
@@ -571,8 +576,8 @@ __global__ void __launch_bounds__(THREADS, 1) pairs_kernel(const __grid_constant
       }
     }
     if (F_TOPK) {
-      for (int r = 0; r < 16; ++r) {
-        const int lr = warp * 16 + r;
+      for (int r = 0; r < RW; ++r) {
+        const int lr = warp * RW + r;
         const int64_t gi = row_base + lr;
         if (gi < P.row1 && lane < k) {
           const int32_t ej = sm.list_j[lr][lane];
@@ -655,8 +660,17 @@ int get_encode_fn(EncodeTiledFn* fn) {
 
 template <int FLAGS>
 int launch_one(unsigned grid, size_t smem, cudaStream_t st, const CUtensorMap& tmap, const Params& P) {
-  DBB_CUDA_TRY(cudaFuncSetAttribute(pairs_kernel<FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  pairs_kernel<FLAGS><<<grid, THREADS, smem, st>>>(tmap, P);
+  // The kernel is templated on the warp count.  16 warps (4x8 register tiles, 128 registers, four warps per
+  // sub-partition) hide the epilogue better (2.1 ms instead of 3.6 ms on C2) but pay 50 % more LDS per FADD2 in the
+  // distance loop (108.8 vs 116.9 G pairs/s without epilogue): the two tie at ~100 G pairs/s, so only the 8-warp
+  // instance is built by default (-DDBB_K2_WARPS16 builds and selects the other; profiles/r01_pairs_notes.md).
+#ifdef DBB_K2_WARPS16
+  DBB_CUDA_TRY(cudaFuncSetAttribute(pairs_kernel<FLAGS, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  pairs_kernel<FLAGS, 16><<<grid, 512, smem, st>>>(tmap, P);
+#else
+  DBB_CUDA_TRY(cudaFuncSetAttribute(pairs_kernel<FLAGS, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  pairs_kernel<FLAGS, 8><<<grid, 256, smem, st>>>(tmap, P);
+#endif
   DBB_CUDA_TRY(cudaGetLastError());
   return DBB_OK;
 }

@@ -4,7 +4,10 @@ import numpy as np, torch
 from dbb_b200 import device, synthetic
 cfg = sys.argv[1] if len(sys.argv) > 1 else 'C2'
 scale = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
-meta = synthetic.make_config(cfg, scale)
+if cfg == 'LONG':
+    meta = synthetic.make_metagenome(seed=9, n_scaffolds=64, min_len=200000, max_len=400000, n_genomes=8, extra_lengths=(5000000,) * int(200 * scale))
+else:
+    meta = synthetic.make_config(cfg, scale)
 d_ascii, seq_off = device.synth_ascii(meta)
 packed = device.pack_ascii(d_ascii, seq_off)
 del d_ascii
