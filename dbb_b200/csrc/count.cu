@@ -363,16 +363,19 @@ struct dbb_count_plan {
 
 namespace {
 
-bool g_tables_uploaded = false;
+bool g_tables_uploaded[64] = {false};   // per device ordinal (constants live in each device's module image)
 
 int upload_tables() {
   // per device would be more general; one device per process is the deployment model (one rank per GPU)
-  if (g_tables_uploaded) return DBB_OK;
+  int dev = 0;
+  DBB_CUDA_TRY(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) { dbb::set_error("device ordinal out of range"); return DBB_ERR_UNSUPPORTED; }
+  if (g_tables_uploaded[dev]) return DBB_OK;
   const dbb::KmerTable& t = dbb::kmer_table();
   DBB_CUDA_TRY(cudaMemcpyToSymbol(c_col_code1, t.col_code1, sizeof(t.col_code1)));
   DBB_CUDA_TRY(cudaMemcpyToSymbol(c_col_code2, t.col_code2, sizeof(t.col_code2)));
   { const char* e = getenv("DBB_K1_DEBUG_SKIP_FLUSH"); int v = (e && *e == '1') ? 1 : 0; DBB_CUDA_TRY(cudaMemcpyToSymbol(c_debug_skip_flush, &v, sizeof(int))); }
-  g_tables_uploaded = true;
+  g_tables_uploaded[dev] = true;
   return DBB_OK;
 }
 
