@@ -397,6 +397,9 @@ def run_ours(args):
         sample = rng.choice(my_n, size=min(16, my_n), replace=False)
         hc = counts.cpu().numpy().astype(np.int64)
         ok = True
+        if not args.no_e2e:                       # every scaffold of the shard, exactly, with the C restatement
+            from oracle import c_oracle
+            ok &= bool(np.array_equal(hc, c_oracle.counts_batch(a_np, seq_off)))
         for i in sample:
             s = d_ascii[int(seq_off[i]):int(seq_off[i + 1])].cpu().numpy()
             ok &= bool(np.array_equal(hc[i], O.seq_counts_np(s)))

@@ -39,7 +39,10 @@ def test_c2_full_size_counts_and_properties():
     tot = c.sum(axis=1, keepdims=True).astype(np.float64)
     f64 = c / tot
     assert (np.abs(f[:, :136] - f64) <= util.FREQ_RTOL * f64).all() and (f[:, 136:] == 0).all()
-    # exact counts against the oracle: a seeded sample + every scaffold with N or lowercase in the first 5000
+    # exact counts of ALL 50 000 scaffolds against the C restatement of the oracle
+    from oracle import c_oracle as C
+    assert np.array_equal(c, C.counts_batch(d_ascii.cpu().numpy(), seq_off))
+    # and against the numpy oracle: a seeded sample + every scaffold with N or lowercase in the first 5000
     rng = np.random.RandomState(0)
     sample = set(rng.choice(n, 150, replace=False).tolist()) | set(np.nonzero(~clean[:5000])[0].tolist())
     sample |= {int(np.argmax(meta.length)), int(np.argmin(meta.length))}

@@ -121,3 +121,25 @@ def test_refine_worker_matches_reference():
     for row, c in zip(nb['refine_rows'], cs[30:]):
         _, _, newBin, bA, bF, bI = O.refine_worker_literal(c, cores, dist)
         assert [newBin, c.length, int(bA), int(bF), int(bI)] == row[1:].tolist()
+
+
+def test_c_restatement_equals_literal_oracle():
+    """oracle/dbb_oracle.c (used for full-size checks) against the Python literal forms."""
+    from oracle import c_oracle as C
+    t, names = C.kmer_table()
+    assert names == O.KMER_COLS and np.array_equal(t, O.code_lut256())
+    kat = util.golden_json('ref_kat_seqs.json')
+    arrs = [np.frombuffer(s.encode(), dtype=np.uint8) for s in kat]
+    off = np.zeros(len(arrs) + 1, np.int64); off[1:] = np.cumsum([a.size for a in arrs])
+    c = C.counts_batch(np.concatenate(arrs), off)
+    for i, s in enumerate(kat):
+        assert c[i].tolist() == O.seq_counts_literal(s)
+    nb, cs = _golden_contigs()
+    from dbb_b200.data import load_td_dist
+    tb = O.DistTables(tdDist=load_td_dist(), tdDistPer=80)
+    sig = nb['tetraSig']
+    bound = tb.tdBound[O.nearest_index_sorted(tb.tdLens, nb['length'])]
+    with np.errstate(invalid='ignore'):
+        dist, mask = C.td_rows(sig, nb['length'], bound, np.arange(len(cs)))
+    assert np.array_equal(mask.astype(np.float64), nb['td_fixedNone_p80'])
+    assert np.allclose(dist, nb['distance'], rtol=0, atol=1e-15, equal_nan=True)
