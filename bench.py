@@ -253,8 +253,9 @@ def run_reference(args):
 
 def workload_config(args, world):
     if getattr(args, 'workload', 'C2') != 'C2':
-        return {'workload': '%s: %d scaffolds in total over %d GPU(s) (strong scaling), tetramer signatures + k=%d TD kNN + TD '
-                            'neighbourhood (per=%d)' % (args.workload, int(1000000 * args.scale), world, K_NN, TD_PER),
+        return {'workload': '%s: %d scaffolds in total over %d GPU(s) (strong scaling), tetramer signatures + k=%d TD kNN + %s '
+                            'neighbourhood (per=%d)' % (args.workload, int((1000000 if args.workload == 'C4' else 250000) * args.scale), world, K_NN,
+                                                        'TD+GC+coverage' if args.workload == 'C3' else 'TD', TD_PER),
                 'k': K_NN, 'td_percentile': TD_PER, 'scale': args.scale,
                 'l2_policy': 'inputs larger than L2', 'parallelism': 'scaffolds LPT-sharded for counting, 1 all-gather (NCCL), row-block kNN'}
     return {'workload': 'C2 per GPU: %d scaffolds x %d GPU(s), 1-100 kb log-uniform (~1.07 Gbp per GPU), tetramer signatures + '
@@ -309,7 +310,14 @@ def run_ours(args):
     total_bp = int(meta.length.sum())
     counts = torch.zeros((my_n, 136), dtype=torch.int32, device=dev)
     freq = torch.zeros((my_n, _lib.SIG_STRIDE), dtype=torch.float32, device=dev)
-    tables = PairTables(meta.length[order], tdDist=load_td_dist(), tdDistPer=TD_PER)
+    if args.workload == 'C3':      # BASELINE.json configs[2]: all three predicates; top-k restricted by the GC and coverage filters
+        tables = PairTables(meta.length[order], GC=meta.gc_obs[order], coverage=meta.coverage[order], tdDist=load_td_dist(),
+                            tdDistPer=TD_PER, gcDist=synthetic.synthetic_gc_dist(), gcDistPer=TD_PER,
+                            covDist=synthetic.synthetic_cov_dist(seed=3), covDistPer=TD_PER)
+        topk_filter = device.FILTER_GC | device.FILTER_COV
+    else:
+        tables = PairTables(meta.length[order], tdDist=load_td_dist(), tdDistPer=TD_PER)
+        topk_filter = 0
     dt = device.DevicePairTables(tables, dev)
     shard_counts = [len(p) for p in parts]
     r0, r1 = parallel.row_block(n_total, rank, world)
@@ -324,7 +332,7 @@ def run_ours(args):
         if e: e[1].record()
         sig_all = parallel.all_gather_rows(freq, shard_counts)
         if e: e[2].record()
-        result['knn'] = device.pairs(sig_all, dt, r0, r1, k=K_NN, want_count=True)
+        result['knn'] = device.pairs(sig_all, dt, r0, r1, k=K_NN, topk_filter=topk_filter, want_count=True)
         if e: e[3].record()
 
     for _ in range(max(args.warmup, 3)):
@@ -364,12 +372,12 @@ def run_ours(args):
 
         def e2e_pairs():
             if world == 1:
-                return _pairs.run_pairs_host(h_freq, tables, k=K_NN, want_count=True)
+                return _pairs.run_pairs_host(h_freq, tables, k=K_NN, topk_filter=topk_filter, want_count=True)
             # N > 1: the host-produced signatures are gathered through the device, then the row block runs
             # with its results copied back to the host
             f = torch.from_numpy(h_freq).to(dev, non_blocking=True)
             sig_all = parallel.all_gather_rows(device.pad_signatures(f), shard_counts)
-            res = device.pairs(sig_all, dt, r0, r1, k=K_NN, want_count=True)
+            res = device.pairs(sig_all, dt, r0, r1, k=K_NN, topk_filter=topk_filter, want_count=True)
             return {k_: v.cpu() for k_, v in res.items()}
 
         e2e_steps = max(1, min(args.steps, 5))
@@ -474,7 +482,7 @@ def main():
     ap.add_argument('--cpu-seconds', type=float, default=8.0, help='target wall time of each CPU-baseline leg')
     ap.add_argument('--no-cpu', action='store_true', help='skip the CPU baseline leg')
     ap.add_argument('--no-e2e', action='store_true', help='skip the host-buffer end-to-end leg (large exploratory workloads)')
-    ap.add_argument('--workload', default='C2', choices=['C2', 'C4'], help='C2 = the benchmark of record (weak scaling); C4 = 1M scaffolds, strong scaling')
+    ap.add_argument('--workload', default='C2', choices=['C2', 'C3', 'C4'], help='C2 = the benchmark of record (weak scaling); C3 = 250k scaffolds with GC + coverage filters, C4 = 1M scaffolds (both strong scaling)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)
