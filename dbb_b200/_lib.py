@@ -82,7 +82,7 @@ def lib():
     if _LIB is None:
         if not os.path.exists(LIB_PATH):
             raise DbbError('%s is not built (run `python -m dbb_b200.build`); dbb_b200 has no CPU fallback' % LIB_PATH)
-        L = ctypes.CDLL(LIB_PATH)
+        L = ctypes.CDLL(os.environ.get('DBB_LIB_PATH', LIB_PATH))   # override: A/B runs of two builds
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(L, name)
             fn.restype = res

@@ -37,13 +37,19 @@ namespace {
 constexpr int TILE = 128;
 constexpr int KCH = 28;                      // floats per K chunk
 constexpr int NKC = DBB_SIG_STRIDE / KCH;    // 5
-constexpr int NSTAGE = 4;
+#ifndef DBB_K2_NSTAGE
+#define DBB_K2_NSTAGE 4
+#endif
+#ifndef DBB_K2_QTOTAL
+#define DBB_K2_QTOTAL 5120
+#endif
+constexpr int NSTAGE = DBB_K2_NSTAGE;        // <= NKC (the column-scalar double buffer relies on it)
 constexpr int CHUNK_BYTES = TILE * KCH * 4;  // 14336
 constexpr int MAX_WARPS = 16;                // the kernel is instantiated for 8 warps (8x8 register tiles, <= 255
                                              // registers) and 16 warps (4x8 tiles, <= 128 registers, 4 warps per sub-partition)
 constexpr int PREFETCH = 2;                  // B chunks in flight ahead of the consumers
 constexpr int LIST_K = DBB_MAX_K;            // list slots per row
-constexpr int QTOTAL = 5120;                 // queue entries per CTA; per warp QTOTAL / WARPS (>= 256 + one row pair's pushes)
+constexpr int QTOTAL = DBB_K2_QTOTAL;                 // queue entries per CTA; per warp QTOTAL / WARPS (>= 256 + one row pair's pushes)
 
 struct RowScalars {       // staged in shared memory per row tile
   int32_t len;
@@ -51,6 +57,18 @@ struct RowScalars {       // staged in shared memory per row tile
   int32_t gcm, gcl, covl;
   int32_t pad;
   double gc, cov;
+};
+
+// Per-column scalars of one column tile, staged once per CTA by bulk copies that complete on the same
+// mbarrier as the tile's first B chunk (double-buffered by tile parity, see issue_chunk()).
+struct ColScalars {
+  alignas(16) float tdb[TILE];
+  alignas(16) int32_t len[TILE];
+  alignas(16) int32_t gcm[TILE];
+  alignas(16) int32_t gcl[TILE];
+  alignas(16) int32_t covl[TILE];
+  alignas(16) double gc[TILE];
+  alignas(16) double cov[TILE];
 };
 
 struct Params {
@@ -65,7 +83,10 @@ struct Params {
   // work items: row tiles [0, n_full_rt) are swept over all columns by one CTA; each remaining row tile is
   // split into n_seg column segments (separate items) whose partial results are merged afterwards
   int32_t n_full_rt, n_seg, n_items, debug_skip_epilogue;
+  int32_t opaque_zero;         // always 0 (see the k4 loop)
+  int32_t skew_cycles;
   uint32_t* item_counter;
+  unsigned long long* stats;   // profiling builds only (-DDBB_K2_STATS, run with DBB_K2_STATS=1): [0] queued pairs, [1] drains, [2] top-k candidates
   int32_t* part_idx; float* part_dist; int32_t* part_cnt; int64_t* part_bp;
 };
 
@@ -74,22 +95,22 @@ struct SmemLayout {
   alignas(128) float b[NSTAGE][TILE][KCH];
   float list_d[TILE][LIST_K];
   int32_t list_j[TILE][LIST_K];
-  float qd[QTOTAL];                       // per-warp queue of pairs that may be a neighbour or a top-k candidate
-                                         //   (the every-pair path reuses the first 256 entries as its scratch)
-  uint32_t qcode[QTOTAL];                //   (row within the warp's rows) << 7 | (column within the tile)
+  float2 q[QTOTAL];                      // per-warp queue of pairs that may be a neighbour or a top-k candidate:
+                                         //   .x = distance, .y = bits of (row within the warp's rows) << 7 | (column
+                                         //   within the tile); the every-pair path uses the first 256 .x as scratch
   RowScalars rows[TILE];
   uint32_t bp_lo[TILE], bp_hi[TILE];     // neighbourhood base pairs per row (64-bit as two native 32-bit atomics)
   int32_t cnt[TILE];                     // neighbourhood size per row
   float thr[TILE];                       // current k-th best distance per row (+inf until k found)
   int32_t qn[MAX_WARPS];                 // queue fill per warp
-  float ctdb[MAX_WARPS][TILE];           // per-warp copy of the current column tile's TD bounds and lengths:
-  int32_t clen[MAX_WARPS][TILE];         //   requested before the FADD2 loop, so their latency hides behind it
+  ColScalars cols[2];                    // column scalars of tile ct live in cols[ct & 1]
   alignas(8) uint64_t full[NSTAGE];
   uint64_t empty[NSTAGE];
   uint64_t a_full;
   int32_t item;
 };
 
+static_assert(NSTAGE <= NKC, "column-scalar double buffer needs NSTAGE <= NKC");
 static_assert(sizeof(SmemLayout) <= 232448, "SmemLayout exceeds the 227 KB per-CTA shared memory limit");
 
 // ---- mbarrier / TMA primitives ------------------------------------------------------------------
@@ -120,15 +141,46 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
       :: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y) : "memory");
 }
 
+// 1-D bulk copy global -> shared (bytes and both addresses multiples of 16), completing on an mbarrier
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// Stages `v` elements of a per-scaffold array into shared memory: the 16-byte-granular part as one bulk copy
+// (returned byte count joins the mbarrier's expected transaction bytes), the <16-byte tail of the last,
+// partial column tile by the calling thread (ordered before its arrive on the barrier).
+template <typename T>
+__device__ __forceinline__ uint32_t stage_cols(T* dst, const T* base, int64_t c0, int v, uint64_t* bar, bool issue) {
+  if (base == nullptr) return 0u;
+  const T* src = base + c0;
+  const uint32_t bytes = ((uint32_t)v * (uint32_t)sizeof(T)) & ~15u;
+  if (!issue) {
+    for (int e = (int)(bytes / sizeof(T)); e < v; ++e) dst[e] = src[e];
+  } else if (bytes) {
+    bulk_load_1d(dst, src, bytes, bar);
+  }
+  return bytes;
+}
+
 __device__ __forceinline__ float2 absdiff_acc(float2 acc, float2 a, float2 b) {
   float2 d = __fadd2_rn(a, make_float2(-b.x, -b.y));
   return __fadd2_rn(acc, make_float2(fabsf(d.x), fabsf(d.y)));
 }
 
+// The dynamic shared memory of the CTA *is* the SmemLayout.  Every function re-derives it from the extern array
+// (instead of taking a reference parameter) so that the compiler keeps the shared address space: a generic
+// reference costs LD + QSPC-guarded atomics in the out-of-line slow paths.
+extern __shared__ __align__(128) uint8_t smem_raw[];
+__device__ __forceinline__ SmemLayout& smem() { return *reinterpret_cast<SmemLayout*>(smem_raw); }
+
 __device__ __forceinline__ void add_bp(SmemLayout& sm, int lr, uint32_t v) {
   const uint32_t old = atomicAdd(&sm.bp_lo[lr], v);
   if (old + v < old) atomicAdd(&sm.bp_hi[lr], 1u);
 }
+
+__device__ __forceinline__ bool cov_predicate(double cu, double cc, double lo, double hi);
 
 // warp-cooperative insertion of (d, c) into the sorted list of `row`; returns the new k-th best
 __device__ __forceinline__ float list_insert(SmemLayout& sm, int row, float d, int32_t c, int k, int lane) {
@@ -152,8 +204,10 @@ __device__ __forceinline__ float list_insert(SmemLayout& sm, int row, float d, i
 // evaluates the predicates of the 2 x 128 pairs whose distances sit in sm.scratch[warp], updates the
 // per-row counts / base pairs / masks / top-k lists.  Whole warp, lanes 0-15 -> row lr0, 16-31 -> lr0+1.
 template <int FLAGS, int WARPS>
-__device__ __noinline__ void process_row_pair(SmemLayout& sm, const Params& P, int warp, int lane, int lr0,
+__device__ __noinline__ void process_row_pair(const Params& P, int par, int warp, int lane, int lr0,
                                               int64_t row_base, int64_t col_base) {
+  SmemLayout& sm = smem();
+  const ColScalars& cs = sm.cols[par];
   constexpr bool F_TD = (FLAGS & 1) != 0, F_GCCOV = (FLAGS & 2) != 0, F_MASK = (FLAGS & 4) != 0, F_TOPK = (FLAGS & 8) != 0;
   constexpr int QCAP = QTOTAL / WARPS;
   const int ty = lane >> 4, tx = lane & 15;
@@ -166,29 +220,27 @@ __device__ __noinline__ void process_row_pair(SmemLayout& sm, const Params& P, i
   const int k = P.k;
   #pragma unroll 1
   for (int j = 0; j < 8; ++j) {
-    const float d = sm.qd[warp * QCAP + (j * 32 + lane)];
+    const float d = sm.q[warp * QCAP + (j * 32 + lane)].x;
     const int64_t cj = col_base + tx + 16 * j;
     const bool col_ok = cj < n;
     int32_t len_j = 0;
     bool p_td = col_ok, p_gc = col_ok, p_cov = col_ok;
     if (col_ok) {
-      len_j = __ldg(P.length + cj);
+      const int c = tx + 16 * j;
+      len_j = cs.len[c];
       const bool i_core = rs.len > len_j;
-      if (F_TD) p_td = d < (i_core ? __ldg(P.td_bound + cj) : rs.tdb);
+      if (F_TD) p_td = d < (i_core ? cs.tdb[c] : rs.tdb);
       if (has_gc) {
-        const int m = i_core ? rs.gcm : __ldg(P.gc_mbin + cj), l = i_core ? __ldg(P.gc_lbin + cj) : rs.gcl;
+        const int m = i_core ? rs.gcm : cs.gcm[c], l = i_core ? cs.gcl[c] : rs.gcl;
         const double lo = __ldg(P.gc_lo + m * P.gc_nl + l), hi = __ldg(P.gc_hi + m * P.gc_nl + l);
-        const double gj = __ldg(P.gc + cj);
+        const double gj = cs.gc[c];
         const double diff = i_core ? (gj - rs.gc) : (rs.gc - gj);
         p_gc = diff >= lo && diff <= hi;
       }
       if (has_cov) {
-        const double vj = __ldg(P.cov + cj);
-        const double cc = i_core ? rs.cov : vj, cu = i_core ? vj : rs.cov;
-        const int l = i_core ? __ldg(P.cov_lbin + cj) : rs.covl;
-        const double eff = cc > 0 ? cc : 0.1;
-        const double diff = (cu - eff) * 100.0 / eff;
-        p_cov = diff >= __ldg(P.cov_lo + l) && diff <= __ldg(P.cov_hi + l);
+        const double vj = cs.cov[c];
+        const int l = i_core ? cs.covl[c] : rs.covl;
+        p_cov = cov_predicate(i_core ? vj : rs.cov, i_core ? rs.cov : vj, __ldg(P.cov_lo + l), __ldg(P.cov_hi + l));
       }
     }
     const bool all = p_td && p_gc && p_cov;
@@ -234,69 +286,149 @@ __device__ __noinline__ void process_row_pair(SmemLayout& sm, const Params& P, i
   __syncwarp();
 }
 
-// Steady-state slow path: the warp's queue holds (distance, row, column) of the few pairs of this column
-// tile that passed the conservative in-register test.  Lane-parallel predicates and counts, then the
-// (rare) top-k candidates are inserted one at a time, warp-cooperatively.
+// Coverage predicate of one pair (coverageNeighbours.py:42-50, distributions.py:106-127), FP64-exact.  Most pairs
+// sit far from both bounds: an FP32 evaluation whose error margin clears them decides those without the FP64
+// division; anything closer (or non-finite) takes the reference's arithmetic.
+__device__ __forceinline__ bool cov_predicate(double cu, double cc, double lo, double hi) {
+  const double eff = cc > 0 ? cc : 0.1;
+  const double num = cu - eff;
+  const float num32 = (float)num, eff32 = (float)eff;
+  const float d32 = __fdividef(num32 * 100.f, eff32);
+  const float lo32 = (float)lo, hi32 = (float)hi;
+  const float margin = 4e-6f * fmaxf(fabsf(d32), fmaxf(fabsf(lo32), fabsf(hi32))) + 1e-30f;
+  // FP32 error here is < 3e-7 relative; operands outside the comfortable float range, NaN and inf are "uncertain"
+  const bool certain = fabsf(d32 - lo32) > margin && fabsf(d32 - hi32) > margin &&
+                       eff32 > 1e-30f && eff32 < 1e30f && fabsf(num32) < 1e30f;
+  bool p = d32 >= lo32 && d32 <= hi32;
+  if (!certain) {
+    const double diff = num * 100.0 / eff;
+    p = diff >= lo && diff <= hi;
+  }
+  return p;
+}
+
+// Steady-state slow path: the warp's queue holds (distance, row, column) of the pairs of this column tile that
+// passed the conservative in-register test (a few per cent: every TD neighbour is one).  Lane-parallel
+// predicates and counts, then the (rare) top-k candidates are inserted one at a time, warp-cooperatively.
+// With GC / coverage predicates the drain runs in two passes: pass A evaluates the shared-memory-only
+// predicates (TD, coverage) and compacts the survivors in place; pass B looks up the GC bounds (a
+// [mean-GC][length] table in global memory, L2 latency) for those few only.
 template <int FLAGS, int WARPS>
-__device__ __noinline__ void drain_queue(SmemLayout& sm, const Params& P, int warp, int lane, int qn,
+__device__ __noinline__ void drain_queue(const Params& P, int par, int warp, int lane, int qn,
                                          int64_t row_base, int64_t col_base) {
+  SmemLayout& sm = smem();
+  const ColScalars& cs = sm.cols[par];
   constexpr bool F_TD = (FLAGS & 1) != 0, F_GCCOV = (FLAGS & 2) != 0, F_TOPK = (FLAGS & 8) != 0;
   constexpr int QCAP = QTOTAL / WARPS, RW = TILE / WARPS;
+  constexpr uint32_t ALL_BIT = 1u << 31, CAND_BIT = 1u << 30, CODE_MASK = (1u << 11) - 1u;
   const int64_t n = P.n;
   const bool has_gc = F_GCCOV && P.gc != nullptr, has_cov = F_GCCOV && P.cov != nullptr;
   const bool want_cnt = P.count != nullptr || P.neighbour_bp != nullptr;
   const int k = P.k;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  float2* q = &sm.q[warp * QCAP];
+#ifdef DBB_K2_STATS
+  if (P.stats && lane == 0) { atomicAdd(P.stats, (unsigned long long)qn); atomicAdd(P.stats + 1, 1ull); }
+#endif
+
+  if (F_GCCOV) {
+    int w = 0;                             // survivors written so far (w <= base: in-place compaction is safe)
+    #pragma unroll 1
+    for (int base = 0; base < qn; base += 32) {
+      const int e = base + lane;
+      const bool valid = e < qn;
+      const float2 qe = valid ? q[e] : make_float2(INFINITY, 0.f);
+      const float d = qe.x;
+      const uint32_t code = __float_as_uint(qe.y);
+      const int c = (int)(code & 127u);
+      const int lr = warp * RW + (int)(code >> 7);
+      const int64_t cj = col_base + c;
+      const bool col_ok = valid && cj < n;
+      bool p_td = col_ok, p_cov = col_ok;
+      if (col_ok) {
+        const RowScalars rs = sm.rows[lr];
+        const bool i_core = rs.len > cs.len[c];
+        if (F_TD) p_td = d < (i_core ? cs.tdb[c] : rs.tdb);
+        if (has_cov) {
+          const double vj = cs.cov[c];
+          const int l = i_core ? cs.covl[c] : rs.covl;
+          p_cov = cov_predicate(i_core ? vj : rs.cov, i_core ? rs.cov : vj, __ldg(P.cov_lo + l), __ldg(P.cov_hi + l));
+        }
+      }
+      const bool all = want_cnt && p_td && p_cov;
+      bool cand = F_TOPK && col_ok && (cj != row_base + lr) && (d <= sm.thr[lr]);
+      if (P.topk_filter & 1) cand = cand && p_td;
+      if (P.topk_filter & 4) cand = cand && p_cov;
+      const bool keep = all || cand;
+      const uint32_t km = __ballot_sync(0xffffffffu, keep);
+      if (keep) {
+        const int o = w + __popc(km & lt_mask);
+        q[o] = make_float2(d, __uint_as_float(code | (all ? ALL_BIT : 0u) | (cand ? CAND_BIT : 0u)));
+      }
+      w += __popc(km);
+      __syncwarp();
+    }
+    qn = w;
+  }
+
   #pragma unroll 1
   for (int base = 0; base < qn; base += 32) {
     const int e = base + lane;
     const bool valid = e < qn;
-    const float d = valid ? sm.qd[warp * QCAP + (e)] : INFINITY;
-    const uint32_t code = valid ? sm.qcode[warp * QCAP + (e)] : 0u;
-    const int lr = warp * RW + (int)(code >> 7);
-    const int64_t cj = col_base + (code & 127u);
+    const float2 qe = valid ? q[e] : make_float2(INFINITY, 0.f);
+    const float d = qe.x;
+    const uint32_t code = __float_as_uint(qe.y);
+    const int c = (int)(code & 127u);
+    const int lr = warp * RW + (int)((code & CODE_MASK) >> 7);
+    const int64_t cj = col_base + c;
     const int64_t gi = row_base + lr;
-    const bool col_ok = valid && cj < n;
+    bool all, cand;
     int32_t len_j = 0;
-    bool p_td = col_ok, p_gc = col_ok, p_cov = col_ok;
-    if (col_ok) {
-      const RowScalars rs = sm.rows[lr];
-      len_j = sm.clen[warp][code & 127u];
-      const bool i_core = rs.len > len_j;
-      if (F_TD) p_td = d < (i_core ? sm.ctdb[warp][code & 127u] : rs.tdb);
-      if (has_gc) {
-        const int m = i_core ? rs.gcm : __ldg(P.gc_mbin + cj), l = i_core ? __ldg(P.gc_lbin + cj) : rs.gcl;
+    if (F_GCCOV) {
+      // pass B: the GC predicate decides what pass A let through
+      bool p_gc = valid;
+      if (valid) len_j = cs.len[c];
+      if (valid && has_gc) {
+        const RowScalars rs = sm.rows[lr];
+        const bool i_core = rs.len > len_j;
+        const int m = i_core ? rs.gcm : cs.gcm[c], l = i_core ? cs.gcl[c] : rs.gcl;
         const double lo = __ldg(P.gc_lo + m * P.gc_nl + l), hi = __ldg(P.gc_hi + m * P.gc_nl + l);
-        const double gj = __ldg(P.gc + cj);
+        const double gj = cs.gc[c];
         const double diff = i_core ? (gj - rs.gc) : (rs.gc - gj);
         p_gc = diff >= lo && diff <= hi;
       }
-      if (has_cov) {
-        const double vj = __ldg(P.cov + cj);
-        const double cc = i_core ? rs.cov : vj, cu = i_core ? vj : rs.cov;
-        const int l = i_core ? __ldg(P.cov_lbin + cj) : rs.covl;
-        const double eff = cc > 0 ? cc : 0.1;
-        const double diff = (cu - eff) * 100.0 / eff;
-        p_cov = diff >= __ldg(P.cov_lo + l) && diff <= __ldg(P.cov_hi + l);
+      all = (code & ALL_BIT) && p_gc;
+      cand = (code & CAND_BIT) != 0;
+      if (P.topk_filter & 2) cand = cand && p_gc;
+    } else {
+      const bool col_ok = valid && cj < n;
+      bool p_td = col_ok;
+      if (col_ok) {
+        const RowScalars rs = sm.rows[lr];
+        len_j = cs.len[c];
+        if (F_TD) p_td = d < ((rs.len > len_j) ? cs.tdb[c] : rs.tdb);
       }
+      all = want_cnt && p_td;
+      cand = F_TOPK && col_ok && (cj != gi) && (d <= sm.thr[lr]);
+      if (P.topk_filter & 1) cand = cand && p_td;
     }
-    if (want_cnt && p_td && p_gc && p_cov) {
+    if (all) {
       atomicAdd(&sm.cnt[lr], 1);
       add_bp(sm, lr, (uint32_t)len_j);
     }
     if (F_TOPK) {
-      bool cand = col_ok && (cj != gi) && (d <= sm.thr[lr]);
-      if (P.topk_filter & 1) cand = cand && p_td;
-      if (P.topk_filter & 2) cand = cand && p_gc;
-      if (P.topk_filter & 4) cand = cand && p_cov;
       uint32_t m = __ballot_sync(0xffffffffu, cand);
       if (P.debug_skip_epilogue == 3) m = 0;
+#ifdef DBB_K2_STATS
+      if (P.stats && lane == 0 && m) atomicAdd(P.stats + 2, (unsigned long long)__popc(m));
+#endif
       while (m) {
         const int src = __ffs(m) - 1;
         m &= m - 1;
         const int crow = __shfl_sync(0xffffffffu, lr, src);
         const float cd = __shfl_sync(0xffffffffu, d, src);
         const int32_t cc = (int32_t)__shfl_sync(0xffffffffu, (int)cj, src);
-        if (cd <= sm.thr[crow]) {
+        if (cd <= sm.thr[crow]) {          // the list may have tightened since the candidate was flagged
           const float nt = list_insert(sm, crow, cd, cc, k, lane);
           if (lane == 0) sm.thr[crow] = nt;
         }
@@ -307,6 +439,130 @@ __device__ __noinline__ void drain_queue(SmemLayout& sm, const Params& P, int wa
   __syncwarp();
 }
 
+// Steady-state test of one row pair (lanes 0-15: row 2i, lanes 16-31: row 2i+1 of the warp's rows; d0..d7 = the
+// lane's distances to columns tx + 16 j).  A pair is queued only if it can be a TD neighbour (d below the row's or
+// the column's bound -- the exact rule is re-applied in the drain) or can enter the row's top-k (d <= k-th best).
+// On the first tile of a sweep the lists are empty; instead of flooding them with all 128 columns the threshold is
+// the largest of the 16 lanes' m-th smallest distances, m = ceil((k+1)/16): at least k+1 columns pass.
+// Out of line on purpose (one copy of the code instead of eight per column tile); everything it needs arrives in
+// registers -- reading Params here means generic loads behind the call (profiles/r01_pairs_notes.md).
+// flags: bit 0 first tile of the sweep, bit 1 TD neighbours are wanted (counts requested).
+template <int FLAGS, int WARPS>
+__device__ __noinline__ void test_row_pair(int par, int warp, int lane, int i, int flags, int ncol, int k, float d0,
+                                           float d1, float d2, float d3, float d4, float d5, float d6, float d7) {
+  constexpr bool F_TD = (FLAGS & 1) != 0, F_TOPK = (FLAGS & 8) != 0;
+  constexpr int QCAP = QTOTAL / WARPS, RW = TILE / WARPS;
+  SmemLayout& sm = smem();
+  const ColScalars& cs = sm.cols[par];
+  const int ty = lane >> 4, tx = lane & 15;
+  const int lr = warp * RW + 2 * i + ty;
+  const bool td_hot = F_TD && (flags & 2);
+  float d[8] = {d0, d1, d2, d3, d4, d5, d6, d7};
+
+  float thr_i = F_TOPK ? sm.thr[lr] : -INFINITY;
+  if (flags & 1) {
+    const int m = (k + 16) / 16;                         // 1, 2 or 3
+    float m1 = INFINITY, m2 = INFINITY, m3 = INFINITY;   // the lane's three smallest valid distances
+    #pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float v = (tx + 16 * j < ncol && d[j] == d[j]) ? d[j] : INFINITY;
+      const float t1 = fminf(m1, v), c1 = fmaxf(m1, v);
+      const float t2 = fminf(m2, c1), c2 = fmaxf(m2, c1);
+      m1 = t1; m2 = t2; m3 = fminf(m3, c2);
+    }
+    float tau = m == 1 ? m1 : (m == 2 ? m2 : m3);
+    #pragma unroll
+    for (int o = 1; o < 16; o <<= 1) tau = fmaxf(tau, __shfl_xor_sync(0xffffffffu, tau, o));
+    thr_i = tau;
+  }
+  // row-side bound: the row's TD bound or its current k-th best, whichever is larger; column side: the column's
+  // TD bound (-inf beyond the last column, see issue_chunk)
+  const float u = fmaxf(td_hot ? sm.rows[lr].tdb : -INFINITY, thr_i);
+  uint32_t bits = 0;
+  #pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float t = td_hot ? cs.tdb[tx + 16 * j] : -INFINITY;
+    bits |= (d[j] <= u || d[j] <= t) ? (1u << j) : 0u;
+  }
+  if (bits) {
+    int slot = warp * QCAP + atomicAdd(&sm.qn[warp], __popc(bits));    // reserve queue slots
+    const uint32_t code0 = (uint32_t)((2 * i + ty) << 7) | (uint32_t)tx;
+    #pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (bits & (1u << j)) {
+        sm.q[slot] = make_float2(d[j], __uint_as_float(code0 | (uint32_t)(16 * j)));
+        ++slot;
+      }
+    }
+  }
+}
+
+// Producer step (one thread): B chunk (column tile `ctile`, K-chunk `kc`) goes to ring stage qg % NSTAGE once the
+// consumers have released it.  The column scalars of the tile travel with its first chunk into cols[ctile & 1]:
+// that buffer was last read by the epilogues of tile ctile-2, and the empty-barrier wait (chunk qg - NSTAGE, which
+// belongs to tile ctile-1 because NSTAGE <= NKC, has been consumed by every warp) implies those are over.
+// (Inlined: an out-of-line call was 1.5 % slower, profiles/r01_pairs_notes.md.)
+template <int FLAGS>
+__device__ __forceinline__ void issue_chunk(const CUtensorMap* tmap, const Params& P, uint32_t qg, int ctile, int kc) {
+  constexpr bool F_TD = (FLAGS & 1) != 0, F_GCCOV = (FLAGS & 2) != 0;
+  SmemLayout& sm = smem();
+  const bool has_gc = F_GCCOV && P.gc != nullptr, has_cov = F_GCCOV && P.cov != nullptr;
+  const int64_t n = P.n;
+  const uint32_t st = qg % NSTAGE;
+  uint64_t* bar = &sm.full[st];
+  if (qg >= NSTAGE) mbar_wait(&sm.empty[st], ((qg / NSTAGE) - 1) & 1);
+  if (kc != 0) {
+    mbar_arrive_expect_tx(bar, CHUNK_BYTES);
+    tma_load_2d(&sm.b[st][0][0], tmap, kc * KCH, ctile * TILE, bar);
+    return;
+  }
+  ColScalars& cs = sm.cols[ctile & 1];
+  const int64_t c0 = (int64_t)ctile * TILE;
+  if (c0 + TILE <= n) {
+    // full column tile: fixed sizes, no tails
+    const uint32_t bytes = CHUNK_BYTES + TILE * 4 + (F_TD ? TILE * 4 : 0) + (has_gc ? TILE * 16 : 0) + (has_cov ? TILE * 12 : 0);
+    mbar_arrive_expect_tx(bar, bytes);
+    tma_load_2d(&sm.b[st][0][0], tmap, 0, ctile * TILE, bar);
+    bulk_load_1d(cs.len, P.length + c0, TILE * 4, bar);
+    if (F_TD) bulk_load_1d(cs.tdb, P.td_bound + c0, TILE * 4, bar);
+    if (has_gc) {
+      bulk_load_1d(cs.gc, P.gc + c0, TILE * 8, bar);
+      bulk_load_1d(cs.gcm, P.gc_mbin + c0, TILE * 4, bar);
+      bulk_load_1d(cs.gcl, P.gc_lbin + c0, TILE * 4, bar);
+    }
+    if (has_cov) {
+      bulk_load_1d(cs.cov, P.cov + c0, TILE * 8, bar);
+      bulk_load_1d(cs.covl, P.cov_lbin + c0, TILE * 4, bar);
+    }
+    return;
+  }
+  // last, partial tile: 16-byte-granular bulk copies + element tails written by this thread before its arrive;
+  // TD bounds beyond the last column read as -inf (test_row_pair does not check column validity)
+  const int v = (int)(n - c0);
+  if (F_TD) for (int e = v; e < TILE; ++e) cs.tdb[e] = -INFINITY;
+  uint32_t bytes = CHUNK_BYTES;
+  #pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    const bool issue = pass == 1;
+    if (issue) {
+      mbar_arrive_expect_tx(bar, bytes);
+      tma_load_2d(&sm.b[st][0][0], tmap, 0, ctile * TILE, bar);
+    }
+    uint32_t b = stage_cols(cs.len, P.length, c0, v, bar, issue);
+    if (F_TD) b += stage_cols(cs.tdb, P.td_bound, c0, v, bar, issue);
+    if (has_gc) {
+      b += stage_cols(cs.gc, P.gc, c0, v, bar, issue);
+      b += stage_cols(cs.gcm, P.gc_mbin, c0, v, bar, issue);
+      b += stage_cols(cs.gcl, P.gc_lbin, c0, v, bar, issue);
+    }
+    if (has_cov) {
+      b += stage_cols(cs.cov, P.cov, c0, v, bar, issue);
+      b += stage_cols(cs.covl, P.cov_lbin, c0, v, bar, issue);
+    }
+    bytes += b;
+  }
+}
+
 // FLAGS: bit0 TD predicate, bit1 GC and/or coverage predicates, bit2 masks, bit3 top-k
 template <int FLAGS, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1) pairs_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Params P) {
@@ -314,8 +570,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pairs_kernel(const __grid_const
   constexpr int RW = TILE / WARPS;          // rows per warp: 16 or 8
   constexpr int RI = RW / 2;                // rows per lane: 8 or 4 (lane owns rows warp*RW + 2i + ty)
   constexpr int QCAP = QTOTAL / WARPS;
-  extern __shared__ __align__(128) uint8_t smem_raw[];
-  SmemLayout& sm = *reinterpret_cast<SmemLayout*>(smem_raw);
+  SmemLayout& sm = smem();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t n = P.n;
   const int64_t n_rows = P.row1 - P.row0;
@@ -336,14 +591,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pairs_kernel(const __grid_const
   const uint32_t lt_mask = (1u << lane) - 1u;
   uint32_t q = 0;          // B chunks consumed so far by this CTA (ring position / mbarrier phase)
   uint32_t items_done = 0;
-
-  // B chunk `l` of the current item (K-chunk l%5 of column tile ct0 + l/5) goes to ring stage (qbase+l)%NSTAGE
-  auto issue_b = [&](uint32_t qg, int ctile, int kc) {
-    const uint32_t st = qg % NSTAGE;
-    if (qg >= NSTAGE) mbar_wait(&sm.empty[st], ((qg / NSTAGE) - 1) & 1);
-    mbar_arrive_expect_tx(&sm.full[st], CHUNK_BYTES);
-    tma_load_2d(&sm.b[st][0][0], &tmap, kc * KCH, ctile * TILE, &sm.full[st]);
-  };
 
   while (true) {
     __syncthreads();                       // everyone is done with the previous item's A tile and lists
@@ -369,7 +616,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pairs_kernel(const __grid_const
     if (tid == 0) {
       mbar_arrive_expect_tx(&sm.a_full, NKC * CHUNK_BYTES);
       for (int kc = 0; kc < NKC; ++kc) tma_load_2d(&sm.a[kc][0][0], &tmap, kc * KCH, (int32_t)row_base, &sm.a_full);
-      for (uint32_t l = 0; l < (uint32_t)PREFETCH && l < item_chunks; ++l) issue_b(qbase + l, ct0 + (int)(l / NKC), (int)(l % NKC));
+      for (uint32_t l = 0; l < (uint32_t)PREFETCH && l < item_chunks; ++l) issue_chunk<FLAGS>(&tmap, P, qbase + l, ct0 + (int)(l / NKC), (int)(l % NKC));
     }
     // stage row scalars and reset the per-row state of this warp's 16 rows
     if (lane < RW) {
@@ -394,6 +641,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pairs_kernel(const __grid_const
     }
     __syncwarp();
     mbar_wait(&sm.a_full, items_done & 1);
+    if (P.skew_cycles > 0 && warp >= WARPS / 2) {          // experiment: second warp of each sub-partition starts late
+      const long long t0 = clock64();
+      while (clock64() - t0 < P.skew_cycles) { }
+    }
 
     const float* a_base = &sm.a[0][warp * RW + ty][0];
     float4 av[RI];                         // A values of the upcoming k4 step (software pipeline, see below)
@@ -401,28 +652,29 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pairs_kernel(const __grid_const
     for (int i = 0; i < RI; ++i) av[i] = *reinterpret_cast<const float4*>(a_base + (2 * i) * KCH);
 
     uint32_t l = 0;                        // chunk index within the item
+#ifdef DBB_K2_STATS
+    long long t_main = 0, t_test = 0, t_drain = 0, t_mark = clock64();
+#define DBB_LAP(var) { const long long t_now = clock64(); var += t_now - t_mark; t_mark = t_now; }
+#else
+#define DBB_LAP(var)
+#endif
     for (int ct = ct0; ct < ct1; ++ct) {
       float2 acc[RI][8];
       #pragma unroll
       for (int i = 0; i < RI; ++i)
         #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = make_float2(0.f, 0.f);
-      // column scalars of this tile (4 columns per lane), consumed by the epilogue
-      float pre_tdb[4];
-      int32_t pre_len[4];
-      #pragma unroll
-      for (int qq = 0; qq < 4; ++qq) {
-        const int64_t cj = (int64_t)ct * TILE + lane + 32 * qq;
-        pre_tdb[qq] = (F_TD && cj < n) ? __ldg(P.td_bound + cj) : -INFINITY;
-        pre_len[qq] = cj < n ? __ldg(P.length + cj) : 0;
-      }
 
       #pragma unroll 1
       for (int kc = 0; kc < NKC; ++kc, ++q, ++l) {
         const uint32_t st = q % NSTAGE;
+#ifdef DBB_K2_ROTATE
+        if (lane == 0 && warp == (int)(((l + PREFETCH) / NKC) % WARPS) && l + PREFETCH < item_chunks) {
+#else
         if (tid == 0 && l + PREFETCH < item_chunks) {
+#endif
           const uint32_t ln = l + PREFETCH;
-          issue_b(qbase + ln, ct0 + (int)(ln / NKC), (int)(ln % NKC));
+          issue_chunk<FLAGS>(&tmap, P, qbase + ln, ct0 + (int)(ln / NKC), (int)(ln % NKC));
         }
         mbar_wait(&sm.full[st], (q / NSTAGE) & 1);
         const float* bq = &sm.b[st][tx][0];
@@ -431,8 +683,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pairs_kernel(const __grid_const
         // chunks and column tiles and the step never starts by waiting for eight LDS.128.
         // Not unrolled: one k4 step is ~280 instructions (4.4 KB); unrolling all 7 steps of a chunk (31 KB) cost
         // ~25 % in instruction-fetch stalls, unrolling by two was 3 % slower (profiles/r01_pairs_notes.md).
+        // The loop start is a run-time zero on purpose: with a compile-time trip count ptxas carries the
+        // prefetched A registers through ~25 MOVs per step (measured -6 %, profiles/r01_pairs_notes.md).
         #pragma unroll 1
-        for (int k4 = (P.debug_skip_epilogue == 4 && warp >= 4) ? KCH / 4 : 0; k4 < KCH / 4; ++k4) {
+        for (int k4 = P.opaque_zero; k4 < KCH / 4; ++k4) {
           const int nkc = (k4 + 1 < KCH / 4) ? kc : (kc + 1 < NKC ? kc + 1 : 0);
           const int nk4 = (k4 + 1 < KCH / 4) ? k4 + 1 : 0;
           const float* an = a_base + nkc * (TILE * KCH) + nk4 * 4;
@@ -459,12 +713,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pairs_kernel(const __grid_const
         if (lane == 0) mbar_arrive(&sm.empty[st]);
       }
 
+      DBB_LAP(t_main)
       // ---------------- epilogue of this column tile ----------------
       const int64_t col_base = (int64_t)ct * TILE;
-      #pragma unroll
-      for (int qq = 0; qq < 4; ++qq) { sm.ctdb[warp][lane + 32 * qq] = pre_tdb[qq]; sm.clen[warp][lane + 32 * qq] = pre_len[qq]; }
-      __syncwarp();
-      if (P.debug_skip_epilogue == 1 || P.debug_skip_epilogue == 4) {
+      const ColScalars& cs = sm.cols[ct & 1];
+      if (P.debug_skip_epilogue == 1) {
         float keep = 0.f;
         #pragma unroll
         for (int i = 0; i < RI; ++i)
@@ -476,86 +729,47 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pairs_kernel(const __grid_const
         #pragma unroll
         for (int i = 0; i < RI; ++i) {
           #pragma unroll
-          for (int j = 0; j < 8; ++j) sm.qd[warp * QCAP + (j * 32 + lane)] = acc[i][j].x + acc[i][j].y;
+          for (int j = 0; j < 8; ++j) sm.q[warp * QCAP + (j * 32 + lane)].x = acc[i][j].x + acc[i][j].y;
           __syncwarp();
-          process_row_pair<FLAGS, WARPS>(sm, P, warp, lane, warp * RW + 2 * i, row_base, col_base);
+          process_row_pair<FLAGS, WARPS>(P, ct & 1, warp, lane, warp * RW + 2 * i, row_base, col_base);
         }
       } else {
-        // A pair is queued only if it can be a TD neighbour (d below the larger of the two bounds -- the exact
-        // rule is re-applied in the drain) or can enter the row's top-k (d <= k-th best).  On the first tile of
-        // a sweep the lists are empty; instead of flooding them with all 128 columns the threshold is the
-        // largest of the 16 lanes' m-th smallest distances, m = ceil((k+1)/16): at least k+1 columns pass.
-        const bool first_tile = F_TOPK && ct == ct0;
-        float tdb_c[8];
-        bool col_ok[8];
-        #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int64_t cj = col_base + tx + 16 * j;
-          col_ok[j] = cj < n;
-          tdb_c[j] = sm.ctdb[warp][tx + 16 * j];
-        }
-        float tdb_cmax = tdb_c[0];
-        #pragma unroll
-        for (int j = 1; j < 8; ++j) tdb_cmax = fmaxf(tdb_cmax, tdb_c[j]);
+        // steady state: one out-of-line call per row pair (see test_row_pair); a row pair pushes at most 256
+        // entries, so checking the fill after every second one needs 512 free slots
         if (lane == 0) sm.qn[warp] = 0;
         __syncwarp();
+        const int tflags = ((F_TOPK && ct == ct0) ? 1 : 0) | (want_cnt ? 2 : 0);
+        const int ncol = (int)((n - col_base) < (int64_t)TILE ? (n - col_base) : (int64_t)TILE);
         #pragma unroll
         for (int i = 0; i < RI; ++i) {
-          const int lr = warp * RW + 2 * i + ty;
-          float thr_i = F_TOPK ? sm.thr[lr] : -INFINITY;
-          if (first_tile) {
-            const int m = (P.k + 16) / 16;                       // 1, 2 or 3
-            float m1 = INFINITY, m2 = INFINITY, m3 = INFINITY;   // the lane's three smallest valid distances
-            #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float d = acc[i][j].x + acc[i][j].y;
-              d = (col_ok[j] && d == d) ? d : INFINITY;
-              const float t1 = fminf(m1, d), c1 = fmaxf(m1, d);
-              const float t2 = fminf(m2, c1), c2 = fmaxf(m2, c1);
-              m1 = t1; m2 = t2; m3 = fminf(m3, c2);
-            }
-            float tau = m == 1 ? m1 : (m == 2 ? m2 : m3);
-            #pragma unroll
-            for (int o = 1; o < 16; o <<= 1) tau = fmaxf(tau, __shfl_xor_sync(0xffffffffu, tau, o));
-            thr_i = tau;
-          }
-          const float u = fmaxf(F_TD ? sm.rows[lr].tdb : -INFINITY, thr_i);
-          // cheap row test first: the smallest of the lane's 8 distances against the largest of its 8 bounds
-          float dmin = INFINITY;
-          #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float d = acc[i][j].x + acc[i][j].y;
-            acc[i][j].x = d;
-            dmin = fminf(dmin, d);
-          }
-          if (dmin <= fmaxf(u, tdb_cmax)) {
-            uint32_t bits = 0;
-            #pragma unroll
-            for (int j = 0; j < 8; ++j) bits |= (acc[i][j].x <= fmaxf(u, tdb_c[j])) ? (1u << j) : 0u;
-            if (bits) {
-              int slot = atomicAdd(&sm.qn[warp], __popc(bits));    // reserve queue slots (hits are rare)
-              #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                if (bits & (1u << j)) {
-                  sm.qd[warp * QCAP + (slot)] = acc[i][j].x;
-                  sm.qcode[warp * QCAP + (slot)] = (uint32_t)((2 * i + ty) << 7) | (uint32_t)(tx + 16 * j);
-                  ++slot;
-                }
-              }
-            }
-          }
-          __syncwarp();
-          const int qn = sm.qn[warp];
-          if (qn > QCAP - 256) {                                 // one row pair pushes at most 256 entries
-            drain_queue<FLAGS, WARPS>(sm, P, warp, lane, qn, row_base, col_base);
-            if (lane == 0) sm.qn[warp] = 0;
+          test_row_pair<FLAGS, WARPS>(ct & 1, warp, lane, i, tflags, ncol, P.k,
+                                      acc[i][0].x + acc[i][0].y, acc[i][1].x + acc[i][1].y, acc[i][2].x + acc[i][2].y,
+                                      acc[i][3].x + acc[i][3].y, acc[i][4].x + acc[i][4].y, acc[i][5].x + acc[i][5].y,
+                                      acc[i][6].x + acc[i][6].y, acc[i][7].x + acc[i][7].y);
+          if ((i & 1) && i + 1 < RI) {
             __syncwarp();
+            const int qn = sm.qn[warp];
+            if (qn > QCAP - 512) {
+              drain_queue<FLAGS, WARPS>(P, ct & 1, warp, lane, qn, row_base, col_base);
+              if (lane == 0) sm.qn[warp] = 0;
+              __syncwarp();
+            }
           }
         }
+        __syncwarp();
         const int qn = sm.qn[warp];
-        if (qn && P.debug_skip_epilogue != 2) drain_queue<FLAGS, WARPS>(sm, P, warp, lane, qn, row_base, col_base);
+        DBB_LAP(t_test)
+        if (qn && P.debug_skip_epilogue != 2) drain_queue<FLAGS, WARPS>(P, ct & 1, warp, lane, qn, row_base, col_base);
       }
+      DBB_LAP(t_drain)
     }  // column tiles
+#ifdef DBB_K2_STATS
+    if (P.stats && lane == 0) {
+      atomicAdd(P.stats + 3, (unsigned long long)t_main);
+      atomicAdd(P.stats + 4, (unsigned long long)t_test);
+      atomicAdd(P.stats + 5, (unsigned long long)t_drain);
+    }
+#endif
 
     // ---------------- per-row outputs (final for whole sweeps, partial for column segments) -----------
     __syncwarp();
@@ -732,6 +946,10 @@ DBB_EXPORT int dbb_pairs_dev(const dbb_pairs_input* in, int64_t row0, int64_t ro
   DBB_REQUIRE(in->n < (1ll << 31) - TILE, "n too large for int32 indices");
   DBB_REQUIRE(in->sig && in->length, "sig/length are required");
   DBB_REQUIRE(((uintptr_t)in->sig & 15) == 0, "sig must be 16-byte aligned");
+  // the per-scaffold arrays are staged tile by tile with 16-byte-granular bulk copies
+  DBB_REQUIRE((((uintptr_t)in->length | (uintptr_t)in->td_bound | (uintptr_t)in->gc | (uintptr_t)in->gc_mbin |
+                (uintptr_t)in->gc_lbin | (uintptr_t)in->cov | (uintptr_t)in->cov_lbin) & 15) == 0,
+              "per-scaffold arrays must be 16-byte aligned");
   DBB_REQUIRE(out->k >= 0 && out->k <= DBB_MAX_K, "k out of range (0..32)");
   DBB_REQUIRE(!in->gc || (in->gc_mbin && in->gc_lbin && in->gc_lo && in->gc_hi && in->gc_nl > 0), "incomplete GC inputs");
   DBB_REQUIRE(!in->cov || (in->cov_lbin && in->cov_lo && in->cov_hi), "incomplete coverage inputs");
@@ -776,6 +994,8 @@ DBB_EXPORT int dbb_pairs_dev(const dbb_pairs_input* in, int64_t row0, int64_t ro
   P.n_full_rt = (int32_t)n_full;
   P.n_seg = n_seg;
   P.n_items = (int32_t)(n_full + rem * n_seg);
+  P.opaque_zero = 0;
+  { const char* e3 = getenv("DBB_K2_SKEW"); P.skew_cycles = (e3 && *e3) ? atoi(e3) : 0; }
   { const char* e2 = getenv("DBB_K2_DEBUG_SKIP_EPILOGUE"); P.debug_skip_epilogue = (e2 && *e2) ? atoi(e2) : 0; }   // profiling only
   const int64_t split_rows = std::min<int64_t>(rem * TILE, n_rows - n_full * TILE);
   const size_t k_ = (size_t)std::max(out->k, 1);
@@ -799,6 +1019,8 @@ DBB_EXPORT int dbb_pairs_dev(const dbb_pairs_input* in, int64_t row0, int64_t ro
   DBB_CUDA_TRY(cudaMallocAsync((void**)&scratch, total, st));
   DBB_CUDA_TRY(cudaMemsetAsync(scratch, 0, 256, st));
   P.item_counter = (uint32_t*)scratch;
+  static const bool want_stats = [] { const char* e = getenv("DBB_K2_STATS"); return e && *e == '1'; }();
+  P.stats = want_stats ? (unsigned long long*)(scratch + 64) : nullptr;
   P.part_idx = (int32_t*)(scratch + off_idx);
   P.part_dist = (float*)(scratch + off_dist);
   P.part_cnt = (int32_t*)(scratch + off_cnt);
@@ -810,6 +1032,16 @@ DBB_EXPORT int dbb_pairs_dev(const dbb_pairs_input* in, int64_t row0, int64_t ro
   if (rc == DBB_OK && rem > 0 && split_rows > 0) {
     merge_kernel<<<(unsigned)((split_rows + 3) / 4), 128, 0, st>>>(P, n_full * TILE, split_rows);
     if (cudaGetLastError() != cudaSuccess) { dbb::set_error("merge kernel launch failed"); rc = DBB_ERR_CUDA; }
+  }
+  if (want_stats && rc == DBB_OK) {
+    unsigned long long h[6] = {0, 0, 0, 0, 0, 0};
+    cudaMemcpyAsync(h, scratch + 64, sizeof(h), cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    const double pairs = (double)(row1 - row0) * (double)in->n;
+    const double tt = (double)(h[3] + h[4] + h[5]) + 1e-9;
+    fprintf(stderr, "[dbb K2 stats] pairs %.3e queued %llu (%.4f %%) drains %llu top-k candidates %llu | warp cycles: distance loop "
+            "%.1f %% hot test %.1f %% final drain %.1f %%\n", pairs, h[0], 100.0 * (double)h[0] / pairs, h[1], h[2],
+            100.0 * h[3] / tt, 100.0 * h[4] / tt, 100.0 * h[5] / tt);
   }
   cudaFreeAsync(scratch, st);
   return rc;

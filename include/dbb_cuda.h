@@ -91,7 +91,9 @@ int dbb_tetra_signatures_host(const uint8_t* ascii, const int64_t* seq_off, int6
 /* ---- stage 2: all-pairs tetranucleotide distance, neighbour predicates and fused top-k ------------
  * tdNeighbours.py:41-51, gcNeighbours.py:43-52, coverageNeighbours.py:41-50 with the bounds of
  * distributions.py:75-127 resolved ONCE PER SCAFFOLD on the host (the algebraic restatement in
- * SURVEY.md section 8a): every per-pair bound depends only on per-scaffold scalars.              */
+ * SURVEY.md section 8a): every per-pair bound depends only on per-scaffold scalars.
+ * dbb_pairs_dev: sig and every [n] array must be 16-byte aligned (cudaMalloc / torch allocations are);
+ * dbb_pairs_host has no alignment requirement.                                                  */
 typedef struct {
   int64_t n;                   /* scaffolds (columns) */
   const float* sig;            /* [n][DBB_SIG_STRIDE] float32 frequencies, cols 136..139 zero */

@@ -192,3 +192,44 @@ def test_refine_closest_cores_vs_reference_rows_and_oracle():
             assert bool(f & 1) == dist.withinDistGC(unb[i], ocores[k]) and bool(f & 2) == dist.withinDistCov(unb[i], ocores[k])
             assert bool(f & 4) == dist.witinDistTD(O.distance(unb[i].tetraSig, np.asarray(ocores[k].tetraSig)), unb[i])
     assert n_assigned > 100
+
+
+def test_queue_path_equals_mask_path_with_coverages_on_the_bounds():
+    """The count / top-k path (queued pairs, two-pass drain, FP32-screened coverage predicate) must agree with the
+    every-pair mask path and with the FP64 oracle when coverage differences sit exactly on, and one ulp either
+    side of, the percentile bounds (coverageNeighbours.py:42-50 is inclusive on both ends)."""
+    from dbb_b200 import _pairs
+    from dbb_b200.distributions import PairTables
+    meta, sig64 = _metagenome(23, 900)
+    td, gcd, cvd = _dists()
+    n = meta.n_scaffolds
+    rows = list(range(n))
+    probe = PairTables(meta.length, GC=meta.gc_obs, coverage=meta.coverage, tdDist=td, tdDistPer=80, gcDist=gcd,
+                       gcDistPer=80, covDist=cvd, covDistPer=80)
+    cov = np.full(n, 5.0)
+    hi = probe.cov_hi[probe.cov_lbin]
+    lo = probe.cov_lo[probe.cov_lbin]
+    on_hi, on_lo = 5.0 * (1.0 + hi / 100.0), 5.0 * (1.0 + lo / 100.0)
+    sel = np.arange(n) % 8
+    cov = np.where(sel == 1, on_hi, cov)
+    cov = np.where(sel == 2, np.nextafter(on_hi, np.inf), cov)
+    cov = np.where(sel == 3, np.nextafter(on_hi, -np.inf), cov)
+    cov = np.where(sel == 4, on_lo, cov)
+    cov = np.where(sel == 5, np.nextafter(on_lo, -np.inf), cov)
+    cov = np.where(sel == 6, np.nextafter(on_lo, np.inf), cov)
+    cov[7] = 0.0; cov[15] = -3.0; cov[23] = 1e-45; cov[31] = 1e36; cov[39] = 1e300
+    tables = PairTables(meta.length, GC=meta.gc_obs, coverage=cov, tdDist=td, tdDistPer=80, gcDist=gcd,
+                        gcDistPer=80, covDist=cvd, covDistPer=80)
+    filt = _pairs.FILTER_GC | _pairs.FILTER_COV
+    slow = _pairs.run_pairs_host(sig64, tables, k=20, topk_filter=filt, want_count=True, want_cov_mask=True)
+    fast = _pairs.run_pairs_host(sig64, tables, k=20, topk_filter=filt, want_count=True)
+    ot = O.DistTables(gcd, 80, td, 80, cvd, 80)
+    with np.errstate(over='ignore', invalid='ignore'):
+        o_cov = O.cov_rows_np(meta.length, cov, rows, ot, None)
+    assert np.array_equal(util.unpack_mask(slow['cov_mask'], n), o_cov)
+    assert 0.05 < o_cov.mean() < 0.95
+    for key in ('count', 'neighbour_bp', 'idx', 'dist'):
+        assert np.array_equal(fast[key], slow[key]), key
+    cov_only = PairTables(meta.length, coverage=cov, covDist=cvd, covDistPer=80)
+    r = _pairs.run_pairs_host(sig64, cov_only, k=0, want_count=True)
+    assert np.array_equal(r['count'], o_cov.sum(axis=1))
