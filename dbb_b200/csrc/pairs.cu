@@ -18,7 +18,7 @@
 //     (d = a - b ; acc += |d|) -- one FP32 issue slot per pair-dimension instead of two.
 //   * the signature matrix is [n][140] float32 (136 + 4 zero pad = 5 K-chunks of 28 floats); TMA
 //     (cp.async.bulk.tensor.2d) stages [128 rows][28 floats] boxes: the A row tile is resident for a
-//     whole row sweep (5 boxes), B boxes stream through a 4-stage mbarrier ring.  Row pitch 112 B =
+//     whole row sweep (5 boxes), B boxes stream through a 5-stage mbarrier ring.  Row pitch 112 B =
 //     7 x 16 B makes every LDS.128 of the tile walk distinct bank groups.
 //   * epilogue per column tile: predicates + counts from registers, 16-bit mask pieces by warp ballot,
 //     top-k candidates (d <= current k-th best of the row, kept in a register) are rare after the first
@@ -38,16 +38,19 @@ constexpr int TILE = 128;
 constexpr int KCH = 28;                      // floats per K chunk
 constexpr int NKC = DBB_SIG_STRIDE / KCH;    // 5
 #ifndef DBB_K2_NSTAGE
-#define DBB_K2_NSTAGE 4
+#define DBB_K2_NSTAGE 5
 #endif
 #ifndef DBB_K2_QTOTAL
-#define DBB_K2_QTOTAL 5120
+#define DBB_K2_QTOTAL 4864
 #endif
 constexpr int NSTAGE = DBB_K2_NSTAGE;        // <= NKC (the column-scalar double buffer relies on it)
 constexpr int CHUNK_BYTES = TILE * KCH * 4;  // 14336
 constexpr int MAX_WARPS = 16;                // the kernel is instantiated for 8 warps (8x8 register tiles, <= 255
                                              // registers) and 16 warps (4x8 tiles, <= 128 registers, 4 warps per sub-partition)
-constexpr int PREFETCH = 2;                  // B chunks in flight ahead of the consumers
+#ifndef DBB_K2_PREFETCH
+#define DBB_K2_PREFETCH 2
+#endif
+constexpr int PREFETCH = DBB_K2_PREFETCH;                  // B chunks in flight ahead of the consumers
 constexpr int LIST_K = DBB_MAX_K;            // list slots per row
 constexpr int QTOTAL = DBB_K2_QTOTAL;                 // queue entries per CTA; per warp QTOTAL / WARPS (>= 256 + one row pair's pushes)
 
