@@ -26,7 +26,11 @@ class PairsInput(ctypes.Structure):
     _fields_ = [('n', c_i64), ('sig', c_vp), ('length', c_vp), ('td_bound', c_vp),
                 ('gc', c_vp), ('gc_mbin', c_vp), ('gc_lbin', c_vp), ('gc_lo', c_vp), ('gc_hi', c_vp),
                 ('gc_nm', c_i32), ('gc_nl', c_i32),
-                ('cov', c_vp), ('cov_lbin', c_vp), ('cov_lo', c_vp), ('cov_hi', c_vp), ('cov_nl', c_i32)]
+                ('cov', c_vp), ('cov_lbin', c_vp), ('cov_lo', c_vp), ('cov_hi', c_vp), ('cov_nl', c_i32),
+                ('metric', c_i32)]
+
+
+METRICS = {'l1': 0, 'manhattan': 0, 'l2': 1, 'euclidean': 1}
 
 
 class PairsOutput(ctypes.Structure):

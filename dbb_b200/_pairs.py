@@ -62,8 +62,11 @@ def _vp(a):
 
 
 def run_pairs_host(sig, tables, k=0, topk_filter=0, want_count=False, want_td_mask=False,
-                   want_gc_mask=False, want_cov_mask=False, row0=0, row1=None):
-    """sig: float[N,136] (any float dtype, converted to float32).  Returns a dict of numpy outputs."""
+                   want_gc_mask=False, want_cov_mask=False, row0=0, row1=None, metric='l1'):
+    """sig: float[N,136] (any float dtype, converted to float32).  Returns a dict of numpy outputs.
+    metric: 'l1' (Manhattan, the reference's) or 'l2' (Euclidean; k-NN with optional TD-style bound only)."""
+    if metric not in _lib.METRICS:
+        raise ValueError("metric must be 'l1' or 'l2'")
     L = _lib.lib()
     sig32 = np.ascontiguousarray(sig, dtype=np.float32)
     n = tables.n
@@ -78,6 +81,7 @@ def run_pairs_host(sig, tables, k=0, topk_filter=0, want_count=False, want_td_ma
     inp.sig = _vp(sig32)
     inp.length = _vp(tables.length)
     inp.td_bound = _vp(tables.td_bound)
+    inp.metric = _lib.METRICS[metric]
     if tables.gc is not None:
         inp.gc, inp.gc_mbin, inp.gc_lbin = _vp(tables.gc), _vp(tables.gc_mbin), _vp(tables.gc_lbin)
         inp.gc_lo, inp.gc_hi = _vp(tables.gc_lo), _vp(tables.gc_hi)

@@ -566,10 +566,13 @@ __device__ __forceinline__ void issue_chunk(const CUtensorMap* tmap, const Param
   }
 }
 
-// FLAGS: bit0 TD predicate, bit1 GC and/or coverage predicates, bit2 masks, bit3 top-k
+// FLAGS: bit0 TD predicate, bit1 GC and/or coverage predicates, bit2 masks, bit3 top-k, bit4 Euclidean distance
+// (sqrt of the sum of squared differences, FFMA2 instead of the second FADD2) instead of the reference's Manhattan
 template <int FLAGS, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1) pairs_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Params P) {
   constexpr bool F_TD = (FLAGS & 1) != 0, F_GCCOV = (FLAGS & 2) != 0, F_MASK = (FLAGS & 4) != 0, F_TOPK = (FLAGS & 8) != 0;
+  constexpr bool F_L2 = (FLAGS & 16) != 0;
+  auto fin = [](float2 a) -> float { return F_L2 ? __fsqrt_rn(a.x + a.y) : a.x + a.y; };   // accumulator -> distance
   constexpr int RW = TILE / WARPS;          // rows per warp: 16 or 8
   constexpr int RI = RW / 2;                // rows per lane: 8 or 4 (lane owns rows warp*RW + 2i + ty)
   constexpr int QCAP = QTOTAL / WARPS;
@@ -702,12 +705,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pairs_kernel(const __grid_const
             #pragma unroll
             for (int i = 0; i < RI; ++i) dd[i] = __fadd2_rn(make_float2(av[i].x, av[i].y), make_float2(-bv.x, -bv.y));
             #pragma unroll
-            for (int i = 0; i < RI; ++i) acc[i][j] = __fadd2_rn(acc[i][j], make_float2(fabsf(dd[i].x), fabsf(dd[i].y)));
+            for (int i = 0; i < RI; ++i)
+              acc[i][j] = F_L2 ? __ffma2_rn(dd[i], dd[i], acc[i][j]) : __fadd2_rn(acc[i][j], make_float2(fabsf(dd[i].x), fabsf(dd[i].y)));
             #pragma unroll
             for (int i = 0; i < RI; ++i) dd[i] = __fadd2_rn(make_float2(av[i].z, av[i].w), make_float2(-bv.z, -bv.w));
             #pragma unroll
             for (int i = 0; i < RI; ++i) {
-              acc[i][j] = __fadd2_rn(acc[i][j], make_float2(fabsf(dd[i].x), fabsf(dd[i].y)));
+              acc[i][j] = F_L2 ? __ffma2_rn(dd[i], dd[i], acc[i][j]) : __fadd2_rn(acc[i][j], make_float2(fabsf(dd[i].x), fabsf(dd[i].y)));
               if (j == 7) av[i] = *reinterpret_cast<const float4*>(an + (2 * i) * KCH);
             }
           }
@@ -732,7 +736,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pairs_kernel(const __grid_const
         #pragma unroll
         for (int i = 0; i < RI; ++i) {
           #pragma unroll
-          for (int j = 0; j < 8; ++j) sm.q[warp * QCAP + (j * 32 + lane)].x = acc[i][j].x + acc[i][j].y;
+          for (int j = 0; j < 8; ++j) sm.q[warp * QCAP + (j * 32 + lane)].x = fin(acc[i][j]);
           __syncwarp();
           process_row_pair<FLAGS, WARPS>(P, ct & 1, warp, lane, warp * RW + 2 * i, row_base, col_base);
         }
@@ -746,9 +750,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pairs_kernel(const __grid_const
         #pragma unroll
         for (int i = 0; i < RI; ++i) {
           test_row_pair<FLAGS, WARPS>(ct & 1, warp, lane, i, tflags, ncol, P.k,
-                                      acc[i][0].x + acc[i][0].y, acc[i][1].x + acc[i][1].y, acc[i][2].x + acc[i][2].y,
-                                      acc[i][3].x + acc[i][3].y, acc[i][4].x + acc[i][4].y, acc[i][5].x + acc[i][5].y,
-                                      acc[i][6].x + acc[i][6].y, acc[i][7].x + acc[i][7].y);
+                                      fin(acc[i][0]), fin(acc[i][1]), fin(acc[i][2]), fin(acc[i][3]), fin(acc[i][4]),
+                                      fin(acc[i][5]), fin(acc[i][6]), fin(acc[i][7]));
           if ((i & 1) && i + 1 < RI) {
             __syncwarp();
             const int qn = sm.qn[warp];
@@ -897,6 +900,7 @@ int launch_pairs(int flags, unsigned grid, size_t smem, cudaStream_t st, const C
 #define DBB_CASE(F) case F: return launch_one<F>(grid, smem, st, tmap, P);
     DBB_CASE(0) DBB_CASE(1) DBB_CASE(2) DBB_CASE(3) DBB_CASE(4) DBB_CASE(5) DBB_CASE(6) DBB_CASE(7)
     DBB_CASE(8) DBB_CASE(9) DBB_CASE(10) DBB_CASE(11) DBB_CASE(12) DBB_CASE(13) DBB_CASE(14) DBB_CASE(15)
+    DBB_CASE(24) DBB_CASE(25)     // Euclidean: k-NN, optionally with the per-scaffold distance bound and counts
 #undef DBB_CASE
   }
   dbb::set_error("bad pairs flags");
@@ -954,6 +958,9 @@ DBB_EXPORT int dbb_pairs_dev(const dbb_pairs_input* in, int64_t row0, int64_t ro
                 (uintptr_t)in->gc_lbin | (uintptr_t)in->cov | (uintptr_t)in->cov_lbin) & 15) == 0,
               "per-scaffold arrays must be 16-byte aligned");
   DBB_REQUIRE(out->k >= 0 && out->k <= DBB_MAX_K, "k out of range (0..32)");
+  DBB_REQUIRE(in->metric == DBB_METRIC_L1 || in->metric == DBB_METRIC_L2, "metric must be DBB_METRIC_L1 or DBB_METRIC_L2");
+  DBB_REQUIRE(in->metric == DBB_METRIC_L1 || (out->k > 0 && !in->gc && !in->cov && !out->td_mask && !out->gc_mask && !out->cov_mask),
+              "the Euclidean metric supports k-NN (k > 0) with the optional distance bound and counts only");
   DBB_REQUIRE(!in->gc || (in->gc_mbin && in->gc_lbin && in->gc_lo && in->gc_hi && in->gc_nl > 0), "incomplete GC inputs");
   DBB_REQUIRE(!in->cov || (in->cov_lbin && in->cov_lo && in->cov_hi), "incomplete coverage inputs");
   const bool masks = out->td_mask || out->gc_mask || out->cov_mask;
@@ -1030,7 +1037,8 @@ DBB_EXPORT int dbb_pairs_dev(const dbb_pairs_input* in, int64_t row0, int64_t ro
   P.part_bp = (int64_t*)(scratch + off_bp);
 
   const unsigned grid = (unsigned)std::min<int64_t>(P.n_items, sms);
-  const int flags = (in->td_bound ? 1 : 0) | ((in->gc || in->cov) ? 2 : 0) | (masks ? 4 : 0) | (out->k > 0 ? 8 : 0);
+  int flags = (in->td_bound ? 1 : 0) | ((in->gc || in->cov) ? 2 : 0) | (masks ? 4 : 0) | (out->k > 0 ? 8 : 0);
+  if (in->metric == DBB_METRIC_L2) flags |= 16;
   rc = launch_pairs(flags, grid, smem, st, tmap, P);
   if (rc == DBB_OK && rem > 0 && split_rows > 0) {
     merge_kernel<<<(unsigned)((split_rows + 3) / 4), 128, 0, st>>>(P, n_full * TILE, split_rows);

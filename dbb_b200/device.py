@@ -141,7 +141,7 @@ def pad_signatures(dense):
     return out
 
 
-def pairs(sig_padded, dt, row0=0, row1=None, k=0, topk_filter=0, want_count=True, masks=()):
+def pairs(sig_padded, dt, row0=0, row1=None, k=0, topk_filter=0, want_count=True, masks=(), metric='l1'):
     """Rows [row0,row1) of the all-pairs problem on the current device/stream.
     sig_padded: float32 cuda [N,140]; dt: DevicePairTables.  Returns a dict of cuda tensors."""
     require_cuda()
@@ -153,6 +153,7 @@ def pairs(sig_padded, dt, row0=0, row1=None, k=0, topk_filter=0, want_count=True
     inp = _lib.PairsInput()
     inp.n = n
     inp.sig, inp.length, inp.td_bound = _p(sig_padded), _p(dt.length), _p(dt.td_bound)
+    inp.metric = _lib.METRICS[metric]
     if dt.gc is not None:
         inp.gc, inp.gc_mbin, inp.gc_lbin, inp.gc_lo, inp.gc_hi = _p(dt.gc), _p(dt.gc_mbin), _p(dt.gc_lbin), _p(dt.gc_lo), _p(dt.gc_hi)
         inp.gc_nm, inp.gc_nl = dt.gc_lo.shape

@@ -33,17 +33,19 @@ class TdNeighbours(object):
         self.rows = _pairs.attach_rows(seqs, 'tdNeighbours', res['td_mask'], self.DENSE_LIMIT)
 
     def knn(self, sig, length, GC=None, cov=None, k=20, tdDist=None, tdDistPer=None, gcDist=None,
-            gcDistPer=None, covDist=None, covDistPer=None, topk_filter=None):
+            gcDistPer=None, covDist=None, covDistPer=None, topk_filter=None, metric='l1'):
         """Returns (idx int32[N,k] padded -1, dist float32[N,k] padded +inf, count int32[N],
         neighbour_bp int64[N]).
 
         Top-k candidates of row i: j != i passing the predicates in ``topk_filter`` (default: the GC
         and coverage filters that are enabled), ordered by (distance asc, j asc).  ``count`` /
-        ``neighbour_bp``: size / total length of {j : all enabled predicates hold}, j == i included."""
+        ``neighbour_bp``: size / total length of {j : all enabled predicates hold}, j == i included.
+        ``metric``: 'l1' is the reference's Manhattan distance (genomicSignatures.py:183-184); 'l2' (Euclidean) is an
+        addition for k-NN callers and cannot be combined with the GC / coverage predicates."""
         tables = PairTables(length, GC=GC, coverage=cov, tdDist=tdDist, tdDistPer=tdDistPer, gcDist=gcDist,
                             gcDistPer=gcDistPer, covDist=covDist, covDistPer=covDistPer,
                             fixedSeqLen=self.fixedSeqLen)
         if topk_filter is None:
             topk_filter = (_pairs.FILTER_GC if gcDist is not None else 0) | (_pairs.FILTER_COV if covDist is not None else 0)
-        res = _pairs.run_pairs_host(sig, tables, k=k, topk_filter=topk_filter, want_count=True)
+        res = _pairs.run_pairs_host(sig, tables, k=k, topk_filter=topk_filter, want_count=True, metric=metric)
         return res['idx'], res['dist'], res['count'], res['neighbour_bp']

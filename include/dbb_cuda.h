@@ -94,6 +94,8 @@ int dbb_tetra_signatures_host(const uint8_t* ascii, const int64_t* seq_off, int6
  * SURVEY.md section 8a): every per-pair bound depends only on per-scaffold scalars.
  * dbb_pairs_dev: sig and every [n] array must be 16-byte aligned (cudaMalloc / torch allocations are);
  * dbb_pairs_host has no alignment requirement.                                                  */
+#define DBB_METRIC_L1 0
+#define DBB_METRIC_L2 1
 typedef struct {
   int64_t n;                   /* scaffolds (columns) */
   const float* sig;            /* [n][DBB_SIG_STRIDE] float32 frequencies, cols 136..139 zero */
@@ -114,6 +116,11 @@ typedef struct {
   const double* cov_lo;        /* [cov_nl] */
   const double* cov_hi;        /* [cov_nl] */
   int32_t cov_nl;
+  /* Distance: DBB_METRIC_L1 = Manhattan, the reference's metric (genomicSignatures.py:183-184, tdNeighbours.py:43).
+   * DBB_METRIC_L2 = Euclidean, an addition for k-NN callers (k > 0; td_bound then bounds the Euclidean distance
+   * by the same shorter-scaffold rule; GC / coverage predicates and masks are not available with it).
+   * Both run on the FP32 CUDA cores; tolerance 2e-6 absolute against FP64 (tests/test_pairs_gpu.py). */
+  int32_t metric;
 } dbb_pairs_input;
 
 typedef struct {

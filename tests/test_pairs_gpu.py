@@ -233,3 +233,37 @@ def test_queue_path_equals_mask_path_with_coverages_on_the_bounds():
     cov_only = PairTables(meta.length, coverage=cov, covDist=cvd, covDistPer=80)
     r = _pairs.run_pairs_host(sig64, cov_only, k=0, want_count=True)
     assert np.array_equal(r['count'], o_cov.sum(axis=1))
+
+
+def test_euclidean_metric_knn_and_bounded_count():
+    """metric='l2' (an addition; the reference only has Manhattan): top-k and the bounded neighbourhood size against
+    float64 numpy, tolerance 2e-6 absolute on the distance as for L1."""
+    from dbb_b200 import _pairs, _lib
+    from dbb_b200.distributions import PairTables
+    meta, sig64 = _metagenome(24, 1100, gmax=20000)
+    n = meta.n_scaffolds
+    rows = list(range(n))
+    td = _dists()[0]
+    tables = PairTables(meta.length, tdDist=td, tdDistPer=80)
+    s = sig64.astype(np.float32).astype(np.float64)
+    from scipy.spatial.distance import cdist
+    d64 = cdist(s, s, 'euclidean')
+    r = _pairs.run_pairs_host(sig64, tables, k=20, want_count=True, metric='l2')
+    util.check_topk(r['idx'], r['dist'].astype(np.float64), d64, rows, 20)
+    shorter_is_i = meta.length[:, None] <= meta.length[None, :]          # ties -> i (tdNeighbours.py:43-47)
+    bound = np.where(shorter_is_i, tables.td_bound[:, None], tables.td_bound[None, :]).astype(np.float64)
+    exact = d64 < bound
+    near = np.abs(d64 - bound) <= util.DIST_ATOL
+    lo = (exact & ~near).sum(axis=1)
+    hi = (exact | near).sum(axis=1)
+    assert ((r['count'] >= lo) & (r['count'] <= hi)).all()
+    assert (r['count'] == exact.sum(axis=1)).mean() > 0.99
+    part = _pairs.run_pairs_host(sig64, tables, k=5, metric='l2', row0=130, row1=700)
+    full5 = _pairs.run_pairs_host(sig64, tables, k=5, metric='l2')
+    assert np.array_equal(part['idx'], full5['idx'][130:700])
+    plain = _pairs.run_pairs_host(sig64, PairTables(meta.length), k=20, metric='l2')     # no bound at all
+    util.check_topk(plain['idx'], plain['dist'].astype(np.float64), d64, rows, 20)
+    with pytest.raises(_lib.DbbError):
+        _pairs.run_pairs_host(sig64, PairTables(meta.length, GC=meta.gc_obs, gcDist=_dists()[1], gcDistPer=80), k=20, metric='l2')
+    with pytest.raises(ValueError):
+        _pairs.run_pairs_host(sig64, tables, k=20, metric='cosine')
