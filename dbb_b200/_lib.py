@@ -60,6 +60,9 @@ SIGNATURES = {
     'dbb_packed_blocks': (c_i64, [c_i64]),
     'dbb_block_offsets': (ctypes.c_int, [c_vp, c_i64, c_vp]),
     'dbb_pack_ascii_dev': (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp]),
+    'dbb_pack_ranges_dev': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    'dbb_split_scaffolds_dev': (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'dbb_base_count_dev': (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),
     'dbb_count_plan_create': (ctypes.c_int, [c_vp, c_i64, ctypes.POINTER(c_vp)]),
     'dbb_count_plan_destroy': (ctypes.c_int, [c_vp]),
     'dbb_count_plan_launches': (ctypes.c_int, [c_vp]),

@@ -8,12 +8,16 @@
 
 namespace {
 
-// one thread per 16-base word of the code plane
+// one thread per 16-base word of the code plane.  Sequence s is ascii[seq_begin[s], seq_end[s]) (for back-to-back
+// sequences seq_end = seq_begin + 1 of one offsets array; for contigs cut out of scaffolds two separate arrays).
+// nmask16 (optional): a third bit plane with the same geometry as the validity plane, bit = base is 'N' or 'n'
+// (what splitScaffolds.py:34 tests), input of the N-run splitter in split.cu.
 __global__ void __launch_bounds__(256) pack_kernel(const uint8_t* __restrict__ ascii,
-                                                   const int64_t* __restrict__ seq_off,
+                                                   const int64_t* __restrict__ seq_begin,
+                                                   const int64_t* __restrict__ seq_end,
                                                    const int64_t* __restrict__ blk_off, int64_t n_seq,
                                                    int64_t total_words, uint32_t* __restrict__ codes,
-                                                   uint16_t* __restrict__ valid16) {
+                                                   uint16_t* __restrict__ valid16, uint16_t* __restrict__ nmask16) {
   int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= total_words) return;
   int64_t blk = g >> 2;
@@ -25,10 +29,10 @@ __global__ void __launch_bounds__(256) pack_kernel(const uint8_t* __restrict__ a
     if (__ldg(blk_off + mid) <= blk) lo = mid; else hi = mid;
   }
   const int64_t s = lo;
-  const int64_t base = __ldg(seq_off + s);
-  const int64_t len = __ldg(seq_off + s + 1) - base;
+  const int64_t base = __ldg(seq_begin + s);
+  const int64_t len = __ldg(seq_end + s) - base;
   const int64_t pos0 = (blk - __ldg(blk_off + s)) * DBB_BLOCK_BASES + q * 16;
-  uint32_t code = 0, vmask = 0;
+  uint32_t code = 0, vmask = 0, nm = 0;
   #pragma unroll
   for (int i = 0; i < 16; ++i) {
     int64_t p = pos0 + i;
@@ -37,10 +41,12 @@ __global__ void __launch_bounds__(256) pack_kernel(const uint8_t* __restrict__ a
     uint32_t c2 = ((ch >> 1) ^ (ch >> 2)) & 3u;          // A0 C1 G2 T3 for the four valid letters
     code = (code << 2) | (ok ? c2 : 0u);
     vmask = (vmask << 1) | ok;
+    nm = (nm << 1) | (uint32_t)((ch | 0x20u) == 'n');
   }
-  codes[g] = code;
+  if (codes) codes[g] = code;
   // uint64 valid word of the block: bit (63-p); as little-endian uint16[4], element 3-q holds bases 16q..16q+15
-  valid16[(blk << 2) + (3 - q)] = (uint16_t)vmask;
+  if (valid16) valid16[(blk << 2) + (3 - q)] = (uint16_t)vmask;
+  if (nmask16) nmask16[(blk << 2) + (3 - q)] = (uint16_t)nm;
 }
 
 __global__ void __launch_bounds__(256) pad_sig_kernel(const float* __restrict__ dense, int64_t n,
@@ -64,7 +70,23 @@ DBB_EXPORT int dbb_pack_ascii_dev(const uint8_t* d_ascii, const int64_t* d_seq_o
   int64_t grid = (words + 255) / 256;
   DBB_REQUIRE(grid < (1ll << 31), "too many blocks for one launch");
   pack_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(
-      d_ascii, d_seq_off, d_blk_off, n_seq, words, (uint32_t*)d_codes, (uint16_t*)d_valid);
+      d_ascii, d_seq_off, d_seq_off + 1, d_blk_off, n_seq, words, (uint32_t*)d_codes, (uint16_t*)d_valid, nullptr);
+  DBB_CUDA_TRY(cudaGetLastError());
+  return DBB_OK;
+}
+
+DBB_EXPORT int dbb_pack_ranges_dev(const uint8_t* d_ascii, const int64_t* d_begin, const int64_t* d_end,
+                                   const int64_t* d_blk_off, int64_t n_seq, int64_t total_blocks,
+                                   void* d_codes, void* d_valid, void* d_nmask, void* stream) {
+  DBB_REQUIRE(n_seq >= 0 && total_blocks >= 0, "negative size");
+  if (total_blocks == 0) return DBB_OK;
+  DBB_REQUIRE(d_ascii && d_begin && d_end && d_blk_off, "NULL device pointer");
+  DBB_REQUIRE(d_codes || d_valid || d_nmask, "no output plane requested");
+  int64_t words = total_blocks * 4;
+  int64_t grid = (words + 255) / 256;
+  DBB_REQUIRE(grid < (1ll << 31), "too many blocks for one launch");
+  pack_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(
+      d_ascii, d_begin, d_end, d_blk_off, n_seq, words, (uint32_t*)d_codes, (uint16_t*)d_valid, (uint16_t*)d_nmask);
   DBB_CUDA_TRY(cudaGetLastError());
   return DBB_OK;
 }

@@ -179,3 +179,58 @@ def pairs(sig_padded, dt, row0=0, row1=None, k=0, topk_filter=0, want_count=True
     if rows and n:
         _lib.check(_lib.lib().dbb_pairs_dev(ctypes.byref(inp), row0, row1, ctypes.byref(out), _stream()))
     return res
+
+
+# ------------------------------------------------------------------------------------------------
+# N2: sequence side of preprocess (split at N runs, base composition, contigs as slices)
+# ------------------------------------------------------------------------------------------------
+
+def pack_ranges(d_ascii, begin, end, want_codes=True, want_nmask=False):
+    """Sequences that are slices ascii[begin[i], end[i]) of one device buffer (host int64 arrays).
+    Returns a PackedBatch; ``.nmask`` (int64 cuda tensor, one word per 64-base block) when requested."""
+    require_cuda()
+    begin = np.ascontiguousarray(begin, dtype=np.int64)
+    end = np.ascontiguousarray(end, dtype=np.int64)
+    packed = PackedBatch(end - begin, d_ascii.device)
+    packed.nmask = torch.empty(max(packed.total_blocks, 1) + 2, dtype=torch.int64, device=d_ascii.device) if want_nmask else None
+    d_b, d_e = torch.from_numpy(begin).to(d_ascii.device), torch.from_numpy(end).to(d_ascii.device)
+    _lib.check(_lib.lib().dbb_pack_ranges_dev(_p(d_ascii), _p(d_b), _p(d_e), _p(packed.d_blk_off), packed.n,
+                                              packed.total_blocks, _p(packed.codes) if want_codes else None,
+                                              _p(packed.valid) if want_codes else None, _p(packed.nmask), _stream()))
+    return packed
+
+
+def split_scaffolds(packed, min_n):
+    """SplitScaffolds.splits (splitScaffolds.py:27-53) for every sequence of a PackedBatch that carries an N plane.
+    Returns (contig_off int64[N+1], begin int64[M], end int64[M]) on the host; positions are relative to the start of
+    their scaffold, contig k of scaffold s sits at contig_off[s] + k."""
+    require_cuda()
+    if packed.nmask is None:
+        raise ValueError('split_scaffolds needs pack_ranges(..., want_nmask=True)')
+    dev = packed.nmask.device
+    d_len = torch.from_numpy(packed.lengths).to(dev)
+    n_contigs = torch.zeros(max(packed.n, 1), dtype=torch.int32, device=dev)
+    L = _lib.lib()
+    _lib.check(L.dbb_split_scaffolds_dev(_p(packed.nmask), _p(d_len), _p(packed.d_blk_off), packed.n, int(min_n), None,
+                                         _p(n_contigs), None, None, _stream()))
+    off = np.zeros(packed.n + 1, dtype=np.int64)
+    off[1:] = np.cumsum(n_contigs[:packed.n].cpu().numpy().astype(np.int64))
+    m = int(off[-1])
+    d_off = torch.from_numpy(off).to(dev)
+    d_begin = torch.empty(max(m, 1), dtype=torch.int64, device=dev)
+    d_end = torch.empty(max(m, 1), dtype=torch.int64, device=dev)
+    _lib.check(L.dbb_split_scaffolds_dev(_p(packed.nmask), _p(d_len), _p(packed.d_blk_off), packed.n, int(min_n), _p(d_off),
+                                         None, _p(d_begin), _p(d_end), _stream()))
+    return off, d_begin[:m].cpu().numpy(), d_end[:m].cpu().numpy()
+
+
+def base_counts(d_ascii, begin, end):
+    """baseCount (seqUtils.py:258-265) of the slices ascii[begin[i], end[i]): int64[n,4] = A, C, G, T+U on the host."""
+    require_cuda()
+    begin = np.ascontiguousarray(begin, dtype=np.int64)
+    end = np.ascontiguousarray(end, dtype=np.int64)
+    n = int(begin.shape[0])
+    out = torch.zeros((max(n, 1), 4), dtype=torch.int64, device=d_ascii.device)
+    d_b, d_e = torch.from_numpy(begin).to(d_ascii.device), torch.from_numpy(end).to(d_ascii.device)
+    _lib.check(_lib.lib().dbb_base_count_dev(_p(d_ascii), _p(d_b), _p(d_e), n, _p(out), _stream()))
+    return out[:n].cpu().numpy()

@@ -69,6 +69,27 @@ int dbb_block_offsets(const int64_t* seq_len, int64_t n_seq, int64_t* blk_off);
 int dbb_pack_ascii_dev(const uint8_t* d_ascii, const int64_t* d_seq_off, const int64_t* d_blk_off,
                        int64_t n_seq, int64_t total_blocks, void* d_codes, void* d_valid, void* stream);
 
+/* Same for sequences that are arbitrary slices ascii[begin[s], end[s]) of one buffer (contigs cut out of their
+ * scaffolds, preprocess.py:158).  Any of d_codes / d_valid / d_nmask may be NULL.  d_nmask is a third bit plane
+ * with the geometry of the validity plane: bit (63 - p) of block word = base p is 'N' or 'n' (splitScaffolds.py:34). */
+int dbb_pack_ranges_dev(const uint8_t* d_ascii, const int64_t* d_begin, const int64_t* d_end, const int64_t* d_blk_off,
+                        int64_t n_seq, int64_t total_blocks, void* d_codes, void* d_valid, void* d_nmask, void* stream);
+
+/* ---- N2: sequence side of the preprocess worker (preprocess.py:118-161) ------------------------------------
+ * dbb_split_scaffolds_dev replaces SplitScaffolds.splits (splitScaffolds.py:27-53) for a batch: scaffold s is cut at
+ * every run of N/n LONGER than min_n that is followed by another base.  Two passes over the N plane of
+ * dbb_pack_ranges_dev: with d_contig_off == NULL it writes the number of contigs per scaffold to d_n_contigs[n_seq];
+ * with d_contig_off[n_seq] (exclusive prefix sum of those counts) it writes d_begin / d_end (positions relative to
+ * the scaffold start, contig k of scaffold s at d_contig_off[s] + k = the reference's '<id>_c<k>').  The reference's
+ * edge behaviour is kept (empty leading contig, trimmed trailing run, dropped one-base tail). */
+int dbb_split_scaffolds_dev(const void* d_nmask, const int64_t* d_seq_len, const int64_t* d_blk_off, int64_t n_seq,
+                            int64_t min_n, const int64_t* d_contig_off, int32_t* d_n_contigs, int64_t* d_begin,
+                            int64_t* d_end, void* stream);
+/* baseCount (seqUtils.py:258-265) for n_ranges slices ascii[begin, end): d_acgt[r] = {A, C, G, T+U}, case-insensitive.
+ * d_ascii must be 4-byte aligned. */
+int dbb_base_count_dev(const uint8_t* d_ascii, const int64_t* d_begin, const int64_t* d_end, int64_t n_ranges,
+                       int64_t* d_acgt, void* stream);
+
 /* A count plan = the device-resident work list (chunks of scaffolds, 16 bytes of metadata each)
  * derived from HOST block offsets.  Build once per batch, run many times. */
 typedef struct dbb_count_plan dbb_count_plan;

@@ -496,3 +496,71 @@ def refine_worker_literal(unbinnedContig, cores, distributions):
     else:
         bInvalid, newBinNum = True, -1
     return closestBin, minDistances, newBinNum, bAssigned, bFailed, bInvalid
+
+
+# ----------------------------------------------------------------------------------------------
+# N2: sequence side of preprocess -- splitScaffolds.py:27-53, seqUtils.py:258-265,
+# preprocess.py:94-100, :118-161 (what a worker computes from the sequence alone)
+# ----------------------------------------------------------------------------------------------
+
+def splits_literal(scaffoldId, scaffold, minN):
+    """splitScaffolds.py:27-53, statement for statement.  Returns an insertion-ordered dict
+    contigId -> [start, end] (the reference's py2 dict has no defined order; callers sort)."""
+    contigs = {}
+    contigCount = 0
+    nCount = 0
+    startIndex = 0
+    nStart = 0
+    for curIndex, ch in enumerate(scaffold):
+        if ch == 'N' or ch == 'n':
+            if nCount == 0:
+                nStart = curIndex
+            nCount += 1
+        else:
+            if nCount > minN:
+                contigs[scaffoldId + '_c' + str(contigCount)] = [startIndex, nStart]
+                contigCount += 1
+                startIndex = curIndex
+            nCount = 0
+    if startIndex != len(scaffold) - 1:
+        if nCount == 0:
+            contigs[scaffoldId + '_c' + str(contigCount)] = [startIndex, len(scaffold)]
+        else:
+            contigs[scaffoldId + '_c' + str(contigCount)] = [startIndex, nStart]
+    return contigs
+
+
+def base_count_literal(seq):
+    """seqUtils.py:258-265: case-insensitive, U counted as T."""
+    testSeq = seq.upper()
+    a = testSeq.count('A')
+    c = testSeq.count('C')
+    g = testSeq.count('G')
+    t = testSeq.count('T') + testSeq.count('U')
+    return a, c, g, t
+
+
+def calculate_gc_literal(seq):
+    """preprocess.py:94-100 (ZeroDivisionError when the sequence has no A/C/G/T/U, as upstream)."""
+    a, c, g, t = base_count_literal(seq)
+    gc = g + c
+    at = a + t
+    return float(gc) / (gc + at)
+
+
+def sequence_stats_literal(scaffoldId, scaffoldSeq, minN):
+    """The sequence-derived part of preprocess.py:118-161 for one scaffold: returns
+    (scaffoldStats [len, GC, sig], contigStats {contigId: [len, GC, sig, start, end]}); the single-contig case
+    stores the scaffold's own statistics under the scaffold id (:160-161; its trailing [0, scaffoldSeq] pair is
+    reported as [0, len])."""
+    contigs = splits_literal(scaffoldId, scaffoldSeq, minN)
+    scaffoldStats = [len(scaffoldSeq), calculate_gc_literal(scaffoldSeq), seq_signature_literal(scaffoldSeq)]
+    contigStats = {}
+    if len(contigs) > 1:
+        for contigId, split in contigs.items():
+            sub = scaffoldSeq[split[0]:split[1]]
+            contigStats[contigId] = [split[1] - split[0], calculate_gc_literal(sub), seq_signature_literal(sub),
+                                     split[0], split[1]]
+    else:
+        contigStats[scaffoldId] = scaffoldStats + [0, len(scaffoldSeq)]
+    return scaffoldStats, contigStats

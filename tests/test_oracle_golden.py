@@ -143,3 +143,17 @@ def test_c_restatement_equals_literal_oracle():
         dist, mask = C.td_rows(sig, nb['length'], bound, np.arange(len(cs)))
     assert np.array_equal(mask.astype(np.float64), nb['td_fixedNone_p80'])
     assert np.allclose(dist, nb["distance"], rtol=0, atol=1e-13, equal_nan=True)   # summation order differs from numpy
+
+
+def test_split_and_base_count_oracle_matches_reference_outputs():
+    """N2 row: the literal restatements of splitScaffolds.py:27-53 and seqUtils.py:258-265 reproduce what the reference's
+    own code returned (tests/golden/make_golden_split.py)."""
+    g = util.golden_json('ref_split.json')
+    seqs = g['seqs']
+    for case in g['splits']:
+        i = case['seq']
+        got = O.splits_literal('s%d' % i, seqs[i], case['minN'])
+        assert got == case['contigs'], (i, case['minN'])
+    for s, want in zip(seqs, g['baseCount']):
+        assert list(O.base_count_literal(s)) == want
+    assert any(v == [0, 0] for c in g['splits'] for v in c['contigs'].values())      # the empty leading contig quirk
