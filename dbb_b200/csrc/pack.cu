@@ -8,8 +8,23 @@
 
 namespace {
 
-// one thread per 16-base word of the code plane.  Sequence s is ascii[seq_begin[s], seq_end[s]) (for back-to-back
-// sequences seq_end = seq_begin + 1 of one offsets array; for contigs cut out of scaffolds two separate arrays).
+// four ASCII bytes (little-endian word, first base in the low byte) -> 8 code bits, 4 validity bits, 4 N bits,
+// first base in the most significant position.  The multiplications gather one field per byte into the top byte;
+// the partial products occupy disjoint bit fields, so no carries occur.
+__device__ __forceinline__ void classify4(uint32_t w, uint32_t& code8, uint32_t& ok4, uint32_t& n4) {
+  const uint32_t ok = __vcmpeq4(w, 0x41414141u) | __vcmpeq4(w, 0x43434343u) | __vcmpeq4(w, 0x47474747u) |
+                      __vcmpeq4(w, 0x54545454u);                       // 0xFF per byte that is A, C, G or T
+  const uint32_t c2 = ((w >> 1) ^ (w >> 2)) & 0x03030303u & ok;      // A0 C1 G2 T3, 0 for everything else
+  code8 = (c2 * 0x40100401u) >> 24;
+  ok4 = ((ok & 0x01010101u) * 0x08040201u) >> 24;
+  n4 = ((__vcmpeq4(w | 0x20202020u, 0x6e6e6e6eu) & 0x01010101u) * 0x08040201u) >> 24;
+}
+
+// One thread per 16-base word of the code plane; a warp covers 512 consecutive bases of the packed layout.
+// Sequence s is ascii[seq_begin[s], seq_end[s]) (for back-to-back sequences seq_end = seq_begin + 1 of one offsets
+// array; for contigs cut out of scaffolds two separate arrays).  Each lane fetches its 16 bytes as the one or two
+// ALIGNED 16-byte chunks that hold them (a chunk that holds a byte of the sequence never leaves the allocation's last
+// 16-byte granule) and realigns in registers, so a warp's loads are coalesced whatever the sequence's offset.
 // nmask16 (optional): a third bit plane with the same geometry as the validity plane, bit = base is 'N' or 'n'
 // (what splitScaffolds.py:34 tests), input of the N-run splitter in split.cu.
 __global__ void __launch_bounds__(256) pack_kernel(const uint8_t* __restrict__ ascii,
@@ -18,30 +33,62 @@ __global__ void __launch_bounds__(256) pack_kernel(const uint8_t* __restrict__ a
                                                    const int64_t* __restrict__ blk_off, int64_t n_seq,
                                                    int64_t total_words, uint32_t* __restrict__ codes,
                                                    uint16_t* __restrict__ valid16, uint16_t* __restrict__ nmask16) {
-  int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= total_words) return;
-  int64_t blk = g >> 2;
-  int q = (int)(g & 3);
-  // last scaffold s with blk_off[s] <= blk  (empty scaffolds share an offset with their successor)
-  int64_t lo = 0, hi = n_seq;            // invariant: blk_off[lo] <= blk < blk_off[hi]
-  while (hi - lo > 1) {
-    int64_t mid = (lo + hi) >> 1;
-    if (__ldg(blk_off + mid) <= blk) lo = mid; else hi = mid;
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // scaffold of the CTA's first word: last s with blk_off[s] <= blk (empty scaffolds share an offset with their
+  // successor); one binary search per CTA, the threads then walk forward from it
+  __shared__ int64_t s_first;
+  if (threadIdx.x == 0) {
+    const int64_t blk_first = ((int64_t)blockIdx.x * blockDim.x) >> 2;
+    int64_t lo = 0, hi = n_seq;          // invariant: blk_off[lo] <= blk_first < blk_off[hi]
+    while (hi - lo > 1) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (__ldg(blk_off + mid) <= blk_first) lo = mid; else hi = mid;
+    }
+    s_first = lo;
   }
-  const int64_t s = lo;
+  __syncthreads();
+  int64_t s = s_first;
+  if (g >= total_words) return;
+  const int64_t blk = g >> 2;
+  const int q = (int)(g & 3);
+  while (__ldg(blk_off + s + 1) <= blk) ++s;
   const int64_t base = __ldg(seq_begin + s);
   const int64_t len = __ldg(seq_end + s) - base;
   const int64_t pos0 = (blk - __ldg(blk_off + s)) * DBB_BLOCK_BASES + q * 16;
+  const int64_t avail = len - pos0;
+  const int v = avail >= 16 ? 16 : (avail > 0 ? (int)avail : 0);     // bases of this word that exist
+  uint32_t w[4] = {0u, 0u, 0u, 0u};
+  if (v > 0) {
+    const uint8_t* src = ascii + base + pos0;
+    const int sh = (int)((uintptr_t)src & 15);
+    const uint4* a0 = reinterpret_cast<const uint4*>(src - sh);
+    const uint4 x = __ldg(a0);
+    uint4 y = make_uint4(0u, 0u, 0u, 0u);
+    if (sh + v > 16) y = __ldg(a0 + 1);
+    const uint32_t r[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+    const int wi = sh >> 2, bs = (sh & 3) * 8;
+    #pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      // r[wi + i], r[wi + i + 1] with wi in 0..3: selected by predication, not by indexing
+      const uint32_t lo32 = wi == 0 ? r[i] : (wi == 1 ? r[i + 1] : (wi == 2 ? r[i + 2] : r[i + 3]));
+      const uint32_t hi32 = wi == 0 ? r[i + 1] : (wi == 1 ? r[i + 2] : (wi == 2 ? r[i + 3] : r[i + 4]));
+      w[i] = __funnelshift_r(lo32, hi32, bs);
+    }
+  }
   uint32_t code = 0, vmask = 0, nm = 0;
   #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    int64_t p = pos0 + i;
-    uint32_t ch = (p < len) ? (uint32_t)__ldg(ascii + base + p) : 0u;
-    uint32_t ok = (ch == 'A') | (ch == 'C') | (ch == 'G') | (ch == 'T');
-    uint32_t c2 = ((ch >> 1) ^ (ch >> 2)) & 3u;          // A0 C1 G2 T3 for the four valid letters
-    code = (code << 2) | (ok ? c2 : 0u);
-    vmask = (vmask << 1) | ok;
-    nm = (nm << 1) | (uint32_t)((ch | 0x20u) == 'n');
+  for (int i = 0; i < 4; ++i) {
+    uint32_t c8, o4, n4;
+    classify4(w[i], c8, o4, n4);
+    code = (code << 8) | c8;
+    vmask = (vmask << 4) | o4;
+    nm = (nm << 4) | n4;
+  }
+  if (v < 16) {                                                      // bytes past the end of the sequence are not bases
+    const uint32_t keep16 = ~(0xFFFFu >> v) & 0xFFFFu;
+    vmask &= keep16;
+    nm &= keep16;
+    code &= v == 0 ? 0u : ~(0xFFFFFFFFu >> (2 * v));
   }
   if (codes) codes[g] = code;
   // uint64 valid word of the block: bit (63-p); as little-endian uint16[4], element 3-q holds bases 16q..16q+15
