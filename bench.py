@@ -252,6 +252,10 @@ def run_reference(args):
 
 
 def workload_config(args, world):
+    if getattr(args, 'workload', 'C2') == 'C5':
+        return {'workload': 'C5: %d contigs of 1-2 kb + 8 scaffolds of 5 Mb (~15 Gbp x %.2f) in total over %d GPU(s) (strong scaling), '
+                            'tetramer signatures only (skewed-length sharding / load-balance stress)' % (int(10000000 * args.scale), args.scale, world),
+                'scale': args.scale, 'l2_policy': 'inputs larger than L2', 'parallelism': 'scaffolds LPT-sharded over the GPUs, no collective'}
     if getattr(args, 'workload', 'C2') != 'C2':
         return {'workload': '%s: %d scaffolds in total over %d GPU(s) (strong scaling), tetramer signatures + k=%d TD kNN + %s '
                             'neighbourhood (per=%d)' % (args.workload, int((1000000 if args.workload == 'C4' else 250000) * args.scale), world, K_NN,
@@ -302,6 +306,9 @@ def run_ours(args):
     mine = parts[rank]
     my_meta = sub_meta(meta, mine, 1000003 * rank)
     n_total = meta.n_scaffolds
+    counting_only = args.workload == 'C5'
+    if counting_only:
+        args.no_e2e = True                           # 15 GB of pinned host ASCII is not worth holding for a stress config
     d_ascii, seq_off = device.synth_ascii(my_meta, dev)
     packed = device.pack_ascii(d_ascii, seq_off)
     plan = device.CountPlan(packed)
@@ -310,7 +317,10 @@ def run_ours(args):
     total_bp = int(meta.length.sum())
     counts = torch.zeros((my_n, 136), dtype=torch.int32, device=dev)
     freq = torch.zeros((my_n, _lib.SIG_STRIDE), dtype=torch.float32, device=dev)
-    if args.workload == 'C3':      # BASELINE.json configs[2]: all three predicates; top-k restricted by the GC and coverage filters
+    if counting_only:
+        tables = dt = None
+        topk_filter = 0
+    elif args.workload == 'C3':      # BASELINE.json configs[2]: all three predicates; top-k restricted by the GC and coverage filters
         tables = PairTables(meta.length[order], GC=meta.gc_obs[order], coverage=meta.coverage[order], tdDist=load_td_dist(),
                             tdDistPer=TD_PER, gcDist=synthetic.synthetic_gc_dist(), gcDistPer=TD_PER,
                             covDist=synthetic.synthetic_cov_dist(seed=3), covDistPer=TD_PER)
@@ -318,7 +328,8 @@ def run_ours(args):
     else:
         tables = PairTables(meta.length[order], tdDist=load_td_dist(), tdDistPer=TD_PER)
         topk_filter = 0
-    dt = device.DevicePairTables(tables, dev)
+    if not counting_only:
+        dt = device.DevicePairTables(tables, dev)
     shard_counts = [len(p) for p in parts]
     r0, r1 = parallel.row_block(n_total, rank, world)
     torch.cuda.synchronize()
@@ -330,9 +341,11 @@ def run_ours(args):
         if e: e[0].record()
         plan.run(counts, freq)
         if e: e[1].record()
-        sig_all = parallel.all_gather_rows(freq, shard_counts)
+        if not counting_only:
+            sig_all = parallel.all_gather_rows(freq, shard_counts)
         if e: e[2].record()
-        result['knn'] = device.pairs(sig_all, dt, r0, r1, k=K_NN, topk_filter=topk_filter, want_count=True)
+        if not counting_only:
+            result['knn'] = device.pairs(sig_all, dt, r0, r1, k=K_NN, topk_filter=topk_filter, want_count=True)
         if e: e[3].record()
 
     for _ in range(max(args.warmup, 3)):
@@ -347,12 +360,18 @@ def run_ours(args):
     torch.cuda.synchronize(); barrier()
     clocks = sampler.stop()
     total_ms = max_over_ranks(t_start.elapsed_time(t_end))
-    ms_count = max_over_ranks(sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps)
+    my_ms_count = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
+    ms_count = max_over_ranks(my_ms_count)
+    per_rank = [[my_ms_count, float(my_bp)]]
+    if dist is not None:
+        t = torch.zeros((world, 2), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(t, torch.tensor([[my_ms_count, float(my_bp)]], dtype=torch.float64, device=dev))
+        per_rank = t.cpu().tolist()
     ms_gather = max_over_ranks(sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps)
     ms_knn = max_over_ranks(sum(e[2].elapsed_time(e[3]) for e in ev) / args.steps)
     ms_step = total_ms / args.steps
     pairs_total = float(n_total) * float(n_total)
-    launches_per_step = plan.launches + int(_lib.lib().dbb_pairs_launches(n_total, r1 - r0))
+    launches_per_step = plan.launches + (0 if counting_only else int(_lib.lib().dbb_pairs_launches(n_total, r1 - r0)))
 
     e2e_s = e2e_count_s = None
     h2d = d2h = 0
@@ -433,18 +452,18 @@ def run_ours(args):
     line = {
         'metric': METRIC,
         'value': total_bp / (ms_count * 1e-3) / 1e9, 'unit': 'Gbp/s',
-        'value2': pairs_total / (ms_knn * 1e-3), 'unit2': 'scaffold-pairs/s',
+        'value2': None if counting_only else pairs_total / (ms_knn * 1e-3), 'unit2': 'scaffold-pairs/s',
         'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_step,
-        'stages_ms': {'signatures': ms_count, 'allgather': ms_gather, 'knn': ms_knn},
-        'pipeline': {'gbp_per_s': total_bp / (ms_step * 1e-3) / 1e9, 'pairs_per_s': pairs_total / (ms_step * 1e-3)},
+        'stages_ms': {'signatures': ms_count, 'allgather': None if counting_only else ms_gather, 'knn': None if counting_only else ms_knn},
+        'pipeline': {'gbp_per_s': total_bp / (ms_step * 1e-3) / 1e9, 'pairs_per_s': None if counting_only else pairs_total / (ms_step * 1e-3)},
         'higher_is_better': True, 'scaling': 'weak' if args.workload == 'C2' else 'strong', 'vs_baseline': None, 'dtype': 'u32 counts / f32 distances',
         'data': 'synthetic', 'config': workload_config(args, world),
         'roofline': {'kernel': 'count_kernel<S> (stage 1, all classes of one launch set)', 'bound': 'hbm', 'achieved': gbs,
-                     'peak': hbm_peak, 'unit': 'GB/s', 'frac': gbs / hbm_peak, 'traffic': traffic.get('count_dram_bytes_per_step'),
+                     'peak': hbm_peak, 'unit': 'GB/s', 'frac': gbs / hbm_peak, 'traffic': traffic.get('count_dram_bytes_per_step') if args.workload == 'C2' and args.scale == 1.0 else None,
                      'algorithmic_bytes': alg_bytes, 'peak_source': peak_src},
-        'roofline_pairs': {'kernel': 'pairs_kernel (stage 2)', 'bound': 'fp32', 'achieved': lane_ops / 1e12,
+        'roofline_pairs': None if counting_only else {'kernel': 'pairs_kernel (stage 2)', 'bound': 'fp32', 'achieved': lane_ops / 1e12,
                            'peak': fp32_peak / 1e12, 'unit': 'T lane-op/s', 'frac': lane_ops / fp32_peak,
-                           'traffic': traffic.get('pairs_dram_bytes_per_step'),
+                           'traffic': traffic.get('pairs_dram_bytes_per_step') if args.workload == 'C2' and args.scale == 1.0 and world == 1 else None,
                            'peak_source': '%d SMs x 128 FP32 lanes x %.0f MHz (272 lane-ops per pair)' % (sm_count, sm_max_mhz)},
         'e2e': None if args.no_e2e else {'value': total_bp / e2e_count_s / 1e9, 'unit': 'Gbp/s', 'value2': pairs_total / max(e2e_s - e2e_count_s, 1e-9),
                 'unit2': 'scaffold-pairs/s', 'ms_per_step': e2e_s * 1e3, 'steps': e2e_steps,
@@ -453,9 +472,11 @@ def run_ours(args):
                 'api': 'dbb_tetra_signatures_host + dbb_pairs_host (pinned host buffers)'},
         'gpu_launches': launches_per_step * args.steps, 'launches_per_step': launches_per_step,
         'clocks': clocks, 'verified_vs_oracle': verified,
-        'shard': {'scaffolds_rank0': my_n, 'bp_rank0': my_bp, 'lpt_imbalance': parallel.imbalance(meta.length, parts)},
+        'shard': {'scaffolds_rank0': my_n, 'bp_rank0': my_bp, 'lpt_imbalance': parallel.imbalance(meta.length, parts),
+                  'count_ms_per_rank': [round(r[0], 4) for r in per_rank], 'bp_per_rank': [int(r[1]) for r in per_rank],
+                  'count_time_imbalance': max(r[0] for r in per_rank) / (sum(r[0] for r in per_rank) / len(per_rank))},
     }
-    if world == 1 and not args.no_cpu:
+    if world == 1 and not args.no_cpu and not counting_only:
         cores = os.cpu_count() or 1
         c = cpu_reference_sample(cpu_sample_meta(args.scale), args.cpu_seconds, cores)
         line['cpu_baseline'] = {
@@ -482,7 +503,7 @@ def main():
     ap.add_argument('--cpu-seconds', type=float, default=8.0, help='target wall time of each CPU-baseline leg')
     ap.add_argument('--no-cpu', action='store_true', help='skip the CPU baseline leg')
     ap.add_argument('--no-e2e', action='store_true', help='skip the host-buffer end-to-end leg (large exploratory workloads)')
-    ap.add_argument('--workload', default='C2', choices=['C2', 'C3', 'C4'], help='C2 = the benchmark of record (weak scaling); C3 = 250k scaffolds with GC + coverage filters, C4 = 1M scaffolds (both strong scaling)')
+    ap.add_argument('--workload', default='C2', choices=['C2', 'C3', 'C4', 'C5'], help='C2 = the benchmark of record (weak scaling); C3 = 250k scaffolds with GC + coverage filters, C4 = 1M scaffolds, C5 = 10M short contigs + 8 x 5 Mb, counting only (all strong scaling)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)
