@@ -87,7 +87,6 @@ struct Params {
   // split into n_seg column segments (separate items) whose partial results are merged afterwards
   int32_t n_full_rt, n_seg, n_items, debug_skip_epilogue;
   int32_t opaque_zero;         // always 0 (see the k4 loop)
-  int32_t skew_cycles;
   uint32_t* item_counter;
   unsigned long long* stats;   // profiling builds only (-DDBB_K2_STATS, run with DBB_K2_STATS=1): [0] queued pairs, [1] drains, [2] top-k candidates
   int32_t* part_idx; float* part_dist; int32_t* part_cnt; int64_t* part_bp;
@@ -647,10 +646,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pairs_kernel(const __grid_const
     }
     __syncwarp();
     mbar_wait(&sm.a_full, items_done & 1);
-    if (P.skew_cycles > 0 && warp >= WARPS / 2) {          // experiment: second warp of each sub-partition starts late
-      const long long t0 = clock64();
-      while (clock64() - t0 < P.skew_cycles) { }
-    }
 
     const float* a_base = &sm.a[0][warp * RW + ty][0];
     float4 av[RI];                         // A values of the upcoming k4 step (software pipeline, see below)
@@ -674,11 +669,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pairs_kernel(const __grid_const
       #pragma unroll 1
       for (int kc = 0; kc < NKC; ++kc, ++q, ++l) {
         const uint32_t st = q % NSTAGE;
-#ifdef DBB_K2_ROTATE
-        if (lane == 0 && warp == (int)(((l + PREFETCH) / NKC) % WARPS) && l + PREFETCH < item_chunks) {
-#else
         if (tid == 0 && l + PREFETCH < item_chunks) {
-#endif
           const uint32_t ln = l + PREFETCH;
           issue_chunk<FLAGS>(&tmap, P, qbase + ln, ct0 + (int)(ln / NKC), (int)(ln % NKC));
         }
@@ -1005,7 +996,6 @@ DBB_EXPORT int dbb_pairs_dev(const dbb_pairs_input* in, int64_t row0, int64_t ro
   P.n_seg = n_seg;
   P.n_items = (int32_t)(n_full + rem * n_seg);
   P.opaque_zero = 0;
-  { const char* e3 = getenv("DBB_K2_SKEW"); P.skew_cycles = (e3 && *e3) ? atoi(e3) : 0; }
   { const char* e2 = getenv("DBB_K2_DEBUG_SKIP_EPILOGUE"); P.debug_skip_epilogue = (e2 && *e2) ? atoi(e2) : 0; }   // profiling only
   const int64_t split_rows = std::min<int64_t>(rem * TILE, n_rows - n_full * TILE);
   const size_t k_ = (size_t)std::max(out->k, 1);
