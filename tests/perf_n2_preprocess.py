@@ -1,4 +1,4 @@
-"""N2 row: device timing of the batched sequence side of preprocess on the C2 input (50 000 scaffolds, 1.07 Gbp,
+"""(Lives under tests/ because its CPU leg imports the oracle.)  N2 row: device timing of the batched sequence side of preprocess on the C2 input (50 000 scaffolds, 1.07 Gbp,
 ASCII resident in HBM), stage by stage, with the algorithmic bytes each stage moves; and the reference's per-scaffold
 loop (oracle restatement of splitScaffolds.py:27-53 + seqUtils.py:258-265) timed on a sample of the same scaffolds."""
 import sys, time
