@@ -67,7 +67,19 @@ __global__ void __launch_bounds__(256) split_kernel(const uint64_t* __restrict__
   if (!write && lane == 0) n_contigs[s] = count;
 }
 
-// One warp per range: case-insensitive A, C, G, T+U counts (seqUtils.py:258-265).
+// One warp per range: case-insensitive A, C, G, T+U counts (seqUtils.py:258-265).  The body streams 16 bytes per
+// lane; per 4-byte word the letters are recognised with the hash-and-compare of pack.cu's classify4 (upper-cased
+// first; 'U' hashes to T's slot and differs from 'T' in bit 0 only, which is masked there), and the four per-byte
+// indicator words are summed byte-wise (SIMD within a register), flushed to 64-bit totals every 255 words.
+__device__ __forceinline__ uint32_t zero_bytes(uint32_t v) {
+  const uint32_t t = (v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+  return ~(t | v) & 0x80808080u;
+}
+__device__ __forceinline__ uint32_t hsum_bytes(uint32_t x) {         // sum of the four bytes of x
+  x = (x & 0x00FF00FFu) + ((x >> 8) & 0x00FF00FFu);
+  return (x & 0xFFFFu) + (x >> 16);
+}
+
 __global__ void __launch_bounds__(256) base_count_kernel(const uint8_t* __restrict__ ascii, const int64_t* __restrict__ begin,
                                                          const int64_t* __restrict__ end, int64_t n_ranges,
                                                          int64_t* __restrict__ acgt) {
@@ -75,34 +87,52 @@ __global__ void __launch_bounds__(256) base_count_kernel(const uint8_t* __restri
   const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (r >= n_ranges) return;
   const int64_t b = begin[r], e = end[r];
-  unsigned long long a = 0, c = 0, g = 0, t = 0;
-  auto add_byte = [&](uint32_t ch) {
-    const uint32_t u = ch & 0xDFu;                                // upper-case the letters
-    a += (u == 'A'); c += (u == 'C'); g += (u == 'G'); t += (u == 'T') | (u == 'U');
+  // totals: letters (any of A C G T U), hash bit 0 set (C, T/U), hash bit 1 set (G, T/U), both (T/U)
+  unsigned long long n_ok = 0, n_lo = 0, n_hi = 0, n_both = 0;
+  uint32_t s_ok = 0, s_lo = 0, s_hi = 0, s_both = 0;                 // byte-wise partial sums
+  int pending = 0;
+  auto add_word = [&](uint32_t w) {
+    const uint32_t u = w & 0xDFDFDFDFu;                              // upper-case the letters
+    const uint32_t t = u >> 1;
+    const uint32_t c2 = (t ^ (t >> 1)) & 0x03030303u;
+    const uint32_t y = (c2 | (c2 >> 4)) & 0x00FF00FFu;
+    const uint32_t expect = __byte_perm(0x54474341u, 0u, (y | (y >> 8)) & 0xFFFFu);
+    const uint32_t both = c2 & (c2 >> 1) & 0x01010101u;              // hash 3: T's slot, where 'U' (0x55) is accepted too
+    const uint32_t ok = zero_bytes((u ^ expect) & ~both) >> 7;
+    s_ok += ok; s_lo += ok & c2; s_hi += ok & (c2 >> 1); s_both += ok & both;
   };
-  // head up to 4-byte alignment, aligned words, tail
+  auto flush = [&]() {
+    n_ok += hsum_bytes(s_ok); n_lo += hsum_bytes(s_lo); n_hi += hsum_bytes(s_hi); n_both += hsum_bytes(s_both);
+    s_ok = s_lo = s_hi = s_both = 0; pending = 0;
+  };
+  auto add_byte = [&](uint32_t ch) { add_word(ch); };                // the three zero bytes above it count nothing
+  // head up to 16-byte alignment, aligned 16-byte vectors, tail
   int64_t p = b;
-  const int64_t head_end = min(e, (b + 3) & ~(int64_t)3);
+  const int64_t head_end = min(e, (b + 15) & ~(int64_t)15);
   if (p + lane < head_end) add_byte(__ldg(ascii + p + lane));
   p = head_end;
-  const int64_t words = (e - p) >> 2;
-  const uint32_t* w32 = reinterpret_cast<const uint32_t*>(ascii + p);
-  for (int64_t i = lane; i < words; i += 32) {
-    const uint32_t u = __ldg(w32 + i) & 0xDFDFDFDFu;
-    a += __popc(__vcmpeq4(u, 0x41414141u)) >> 3;
-    c += __popc(__vcmpeq4(u, 0x43434343u)) >> 3;
-    g += __popc(__vcmpeq4(u, 0x47474747u)) >> 3;
-    t += (__popc(__vcmpeq4(u, 0x54545454u)) + __popc(__vcmpeq4(u, 0x55555555u))) >> 3;
+  const int64_t vecs = (e - p) >> 4;
+  const uint4* v128 = reinterpret_cast<const uint4*>(ascii + p);
+  for (int64_t i = lane; i < vecs; i += 32) {
+    const uint4 v = __ldg(v128 + i);
+    add_word(v.x); add_word(v.y); add_word(v.z); add_word(v.w);
+    pending += 4;
+    if (pending >= 252) flush();
   }
-  p += words * 4;
+  p += vecs * 16;
   if (p + lane < e) add_byte(__ldg(ascii + p + lane));
+  flush();
   #pragma unroll
   for (int d = 16; d > 0; d >>= 1) {
-    a += __shfl_xor_sync(0xffffffffu, a, d); c += __shfl_xor_sync(0xffffffffu, c, d);
-    g += __shfl_xor_sync(0xffffffffu, g, d); t += __shfl_xor_sync(0xffffffffu, t, d);
+    n_ok += __shfl_xor_sync(0xffffffffu, n_ok, d); n_lo += __shfl_xor_sync(0xffffffffu, n_lo, d);
+    n_hi += __shfl_xor_sync(0xffffffffu, n_hi, d); n_both += __shfl_xor_sync(0xffffffffu, n_both, d);
   }
   if (lane == 0) {
-    acgt[4 * r + 0] = (int64_t)a; acgt[4 * r + 1] = (int64_t)c; acgt[4 * r + 2] = (int64_t)g; acgt[4 * r + 3] = (int64_t)t;
+    // hash 0 = A, 1 = C, 2 = G, 3 = T/U
+    acgt[4 * r + 0] = (int64_t)(n_ok - n_lo - n_hi + n_both);
+    acgt[4 * r + 1] = (int64_t)(n_lo - n_both);
+    acgt[4 * r + 2] = (int64_t)(n_hi - n_both);
+    acgt[4 * r + 3] = (int64_t)n_both;
   }
 }
 
@@ -128,7 +158,7 @@ DBB_EXPORT int dbb_base_count_dev(const uint8_t* d_ascii, const int64_t* d_begin
   DBB_REQUIRE(n_ranges >= 0, "negative size");
   if (n_ranges == 0) return DBB_OK;
   DBB_REQUIRE(d_ascii && d_begin && d_end && d_acgt, "NULL device pointer");
-  DBB_REQUIRE(((uintptr_t)d_ascii & 3) == 0, "d_ascii must be 4-byte aligned");
+  DBB_REQUIRE(((uintptr_t)d_ascii & 15) == 0, "d_ascii must be 16-byte aligned");
   const int64_t grid = (n_ranges * 32 + 255) / 256;
   DBB_REQUIRE(grid < (1ll << 31), "too many ranges for one launch");
   base_count_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(d_ascii, d_begin, d_end, n_ranges, d_acgt);

@@ -86,7 +86,7 @@ int dbb_split_scaffolds_dev(const void* d_nmask, const int64_t* d_seq_len, const
                             int64_t min_n, const int64_t* d_contig_off, int32_t* d_n_contigs, int64_t* d_begin,
                             int64_t* d_end, void* stream);
 /* baseCount (seqUtils.py:258-265) for n_ranges slices ascii[begin, end): d_acgt[r] = {A, C, G, T+U}, case-insensitive.
- * d_ascii must be 4-byte aligned. */
+ * d_ascii must be 16-byte aligned. */
 int dbb_base_count_dev(const uint8_t* d_ascii, const int64_t* d_begin, const int64_t* d_end, int64_t n_ranges,
                        int64_t* d_acgt, void* stream);
 
