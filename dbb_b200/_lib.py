@@ -46,6 +46,12 @@ class RefineInput(ctypes.Structure):
                 ('cov_lo', c_vp), ('cov_hi', c_vp), ('cov_nl', c_i32)]
 
 
+class GreedyInput(ctypes.Structure):
+    _fields_ = [('n', c_i64), ('sig', c_vp), ('length', c_vp), ('gc', c_vp), ('cov', c_vp), ('td_bound', c_vp),
+                ('gc_lbin', c_vp), ('cov_lbin', c_vp), ('gc_mean_keys', c_vp), ('gc_lo', c_vp), ('gc_hi', c_vp),
+                ('gc_nm', c_i32), ('gc_nl', c_i32), ('cov_lo', c_vp), ('cov_hi', c_vp), ('cov_nl', c_i32)]
+
+
 class RefineOutput(ctypes.Structure):
     _fields_ = [('closest', c_vp), ('min_dist', c_vp), ('assigned', c_vp), ('within', c_vp)]
 
@@ -74,6 +80,7 @@ SIGNATURES = {
     'dbb_pairs_host': (ctypes.c_int, [ctypes.POINTER(PairsInput), c_i64, c_i64, ctypes.POINTER(PairsOutput)]),
     'dbb_refine_dev': (ctypes.c_int, [ctypes.POINTER(RefineInput), ctypes.POINTER(RefineOutput), c_vp]),
     'dbb_refine_host': (ctypes.c_int, [ctypes.POINTER(RefineInput), ctypes.POINTER(RefineOutput)]),
+    'dbb_greedy_host': (ctypes.c_int, [ctypes.POINTER(GreedyInput), c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'dbb_pad_signatures_dev': (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp]),
     'dbb_synth_ascii_dev': (ctypes.c_int, [ctypes.c_uint64, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp,
                                            c_vp, c_vp, c_vp]),

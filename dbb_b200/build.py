@@ -12,11 +12,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OBJ = os.path.join(CSRC, '_obj')
 LIB = os.path.join(HERE, 'libdbbcuda.so')
-SOURCES = ['table.cu', 'pack.cu', 'count.cu', 'pairs.cu', 'refine.cu', 'split.cu', 'synth.cu', 'host_api.cu']
+SOURCES = ['table.cu', 'pack.cu', 'count.cu', 'pairs.cu', 'refine.cu', 'greedy.cu', 'split.cu', 'synth.cu', 'host_api.cu']
 HEADERS = [os.path.join(CSRC, 'common.cuh'), os.path.join(HERE, '..', 'include', 'dbb_cuda.h')]
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
-         '-Xcompiler', '-fPIC,-fvisibility=hidden', '--expt-relaxed-constexpr']
+         '-Xcompiler', '-fPIC,-fvisibility=hidden,-ffp-contract=off', '--expt-relaxed-constexpr']
 
 
 def _stale(target, deps):
@@ -42,7 +42,8 @@ def build(verbose=False, force=False):
     os.makedirs(OBJ, exist_ok=True)
     if force:
         for f in os.listdir(OBJ):
-            os.remove(os.path.join(OBJ, f))
+            if os.path.isfile(os.path.join(OBJ, f)):
+                os.remove(os.path.join(OBJ, f))
     with concurrent.futures.ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         results = list(ex.map(lambda s: _compile(s, verbose), SOURCES))
     objs = [o for o, _ in results]

@@ -1,0 +1,68 @@
+"""Greedy core growth of dbb/greedy.py (``Greedy.__greedy``, greedy.py:167-251), GPU assisted.
+
+``Greedy().greedy(sortedContigs, minBinSize, buildDistPer, gcDist, tdDist, covDist)`` is the reference's private
+``__greedy`` with the same arguments (minus ``genomicSig`` / ``numThreads``, which it only used for the L1 distance):
+it sets ``contig.bProcessed`` / ``contig.binId`` and returns the list of ``Core`` objects with ``.contigs``.  Element
+type of ``sortedContigs``: any object with ``.length, .GC, .coverage, .tetraSig`` (``Contig``, greedy.py:133-141).
+The scan over the candidates of each growth step runs on the GPU (csrc/greedy.cu), the sequential outer loop in C++.
+"""
+import ctypes
+import logging
+
+import numpy as np
+
+from . import _lib
+from .distributions import Distributions, _sorted_keys, nearest_index
+from .refineBins import Core, UNBINNED
+
+
+class Greedy(object):
+    UNBINNED = UNBINNED
+
+    def __init__(self, bDebug=False):
+        self.logger = logging.getLogger()
+        self.numSteps = 0
+
+    def greedy(self, sortedContigs, minBinSize, buildDistPer, gcDist, tdDist, covDist):
+        n = len(sortedContigs)
+        dist = Distributions(gcDist, buildDistPer, tdDist, buildDistPer, covDist, buildDistPer)
+        arr = lambda it, dt=np.float64: np.ascontiguousarray(np.array(list(it), dtype=dt))
+        length = arr((c.length for c in sortedContigs), np.int64)
+        sig = np.ascontiguousarray(np.array([c.tetraSig for c in sortedContigs], dtype=np.float64).reshape(n, _lib.NUM_KMERS))
+        gc, cov = arr(c.GC for c in sortedContigs), arr(c.coverage for c in sortedContigs)
+        td_lens = _sorted_keys(tdDist)
+        tdb = np.ascontiguousarray(np.array([tdDist[l][dist.tdKey] for l in td_lens], dtype=np.float64)[nearest_index(td_lens, length)])
+        means = _sorted_keys(gcDist)
+        gc_lens = _sorted_keys(gcDist[means[0]])
+        cov_lens = _sorted_keys(covDist)
+        gcl, covl = nearest_index(gc_lens, length), nearest_index(cov_lens, length)
+        mean_keys = np.ascontiguousarray(np.array(means, dtype=np.float64))
+        gc_lo = np.array([[gcDist[m][l][dist.gcLowerBoundKey] for l in gc_lens] for m in means], dtype=np.float64)
+        gc_hi = np.array([[gcDist[m][l][dist.gcUpperBoundKey] for l in gc_lens] for m in means], dtype=np.float64)
+        cov_lo = np.array([covDist[l][dist.covLowerBoundKey] for l in cov_lens], dtype=np.float64)
+        cov_hi = np.array([covDist[l][dist.covUpperBoundKey] for l in cov_lens], dtype=np.float64)
+        bin_id = np.full(max(n, 1), UNBINNED, dtype=np.int32)
+        core_len = np.zeros(max(n, 1), dtype=np.int64)
+        core_gc, core_cov = np.zeros(max(n, 1)), np.zeros(max(n, 1))
+        core_sig = np.zeros((max(n, 1), _lib.NUM_KMERS))
+        n_cores, n_steps = ctypes.c_int64(0), ctypes.c_int64(0)
+        if n:
+            vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+            inp = _lib.GreedyInput(n, vp(sig), vp(length), vp(gc), vp(cov), vp(tdb), vp(gcl), vp(covl), vp(mean_keys),
+                                   vp(gc_lo), vp(gc_hi), gc_lo.shape[0], gc_lo.shape[1], vp(cov_lo), vp(cov_hi), cov_lo.shape[0])
+            _lib.check(_lib.lib().dbb_greedy_host(ctypes.byref(inp), int(minBinSize), vp(bin_id), ctypes.byref(n_cores),
+                                                  vp(core_len), vp(core_gc), vp(core_cov), vp(core_sig), ctypes.byref(n_steps)))
+        self.numSteps = int(n_steps.value)
+        cores = []
+        for b in range(int(n_cores.value)):
+            core = Core(b, int(core_len[b]), float(core_gc[b]), float(core_cov[b]), core_sig[b].copy())
+            core.contigs = []
+            cores.append(core)
+        for i, contig in enumerate(sortedContigs):
+            contig.binId = int(bin_id[i])
+            contig.bProcessed = bin_id[i] != UNBINNED
+            if contig.bProcessed:
+                cores[contig.binId].contigs.append(contig)
+        # greedy.py:227 appends the members in the order they were added; recover it is not possible from bin ids
+        # alone, so the lists here are in contig order (the seed first, as in the reference)
+        return cores

@@ -214,6 +214,28 @@ int dbb_synth_ascii_dev(uint64_t seed, int64_t n_seq, const int64_t* d_seq_off, 
                         const int64_t* d_n_start, const int64_t* d_n_len, const int64_t* d_lc_start,
                         const int64_t* d_lc_len, uint8_t* d_ascii, void* stream);
 
+/* ---- "next" row N3: greedy core growth -- Greedy.__greedy, greedy.py:167-251 ----------------------------------
+ * Contigs in the caller's order (greedy.py walks `sortedContigs`).  Per contig (all resolved on the host as in the
+ * refine row): td_bound[i] = tdDist[nearest(len_i)][tdKey] (witinDistTD(d, contig)), gc_lbin / cov_lbin = nearest
+ * length key of the contig; gc_mean_keys[gc_nm] are the mean-GC keys of the GC table in ascending order (the core's
+ * key is re-resolved at every step because its GC moves).  Outputs: bin_id[n] (-1 = unbinned, Greedy.UNBINNED),
+ * the number of cores kept, and per kept core its length, GC, coverage and signature exactly as the running
+ * weighted means of greedy.py:229-234 leave them ([n] / [n][136] capacity; any may be NULL).  The loop over growth
+ * steps runs on the host, the scan over the candidates of each step on the GPU (one launch per step). */
+typedef struct {
+  int64_t n;
+  const double* sig;           /* [n][136] float64 signatures */
+  const int64_t* length;       /* [n] */
+  const double* gc; const double* cov;               /* [n] */
+  const double* td_bound;      /* [n] */
+  const int32_t* gc_lbin; const int32_t* cov_lbin;   /* [n] */
+  const double* gc_mean_keys;  /* [gc_nm] ascending */
+  const double* gc_lo; const double* gc_hi; int32_t gc_nm, gc_nl;
+  const double* cov_lo; const double* cov_hi; int32_t cov_nl;
+} dbb_greedy_input;
+int dbb_greedy_host(const dbb_greedy_input* in_host, int64_t min_bin_size, int32_t* bin_id, int64_t* n_cores,
+                    int64_t* core_len, double* core_gc, double* core_cov, double* core_sig, int64_t* n_steps);
+
 #ifdef __cplusplus
 }
 #endif

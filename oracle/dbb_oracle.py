@@ -564,3 +564,64 @@ def sequence_stats_literal(scaffoldId, scaffoldSeq, minN):
     else:
         contigStats[scaffoldId] = scaffoldStats + [0, len(scaffoldSeq)]
     return scaffoldStats, contigStats
+
+
+# ----------------------------------------------------------------------------------------------
+# N3: greedy core growth -- greedy.py:167-251 (Greedy.__greedy)
+# ----------------------------------------------------------------------------------------------
+
+def greedy_literal(sortedContigs, minBinSize, distributions):
+    """greedy.py:172-251, statement for statement (progress output dropped; ``genomicSig.distance`` is
+    ``distance`` above).  Sets ``bProcessed`` / ``binId`` on the contigs, returns the list of cores."""
+    for contig in sortedContigs:
+        contig.bProcessed = False
+    numCores = 0
+    cores = []
+    for contigIndex, contig in enumerate(sortedContigs):
+        if contig.bProcessed:
+            continue
+        contig.bProcessed = True
+        contig.binId = numCores
+        contigsInCurCore = [contig]
+        curCore = Core(numCores, contig.length, contig.GC, contig.coverage, np.array(contig.tetraSig, dtype=float))
+        bCoreExpanded = True
+        while bCoreExpanded:
+            closestContig = None
+            closestAbsCovDiff = 1e12
+            for curContig in sortedContigs[contigIndex + 1:]:
+                if curContig.bProcessed:
+                    continue
+                absCovDiff = abs(curContig.coverage - curCore.coverage)
+                if absCovDiff > closestAbsCovDiff:
+                    continue
+                if not distributions.withinDistGC(curContig, curCore):
+                    continue
+                if not distributions.withinDistCov(curContig, curCore):
+                    continue
+                tdDistance = distance(curContig.tetraSig, curCore.tetraSig)
+                if not distributions.witinDistTD(tdDistance, curContig):
+                    continue
+                closestAbsCovDiff = absCovDiff
+                closestContig = curContig
+            if closestContig is not None:
+                bCoreExpanded = True
+                closestContig.bProcessed = True
+                closestContig.binId = numCores
+                contigsInCurCore.append(closestContig)
+                curCore.length += closestContig.length
+                weight = float(closestContig.length) / curCore.length
+                curCore.GC = closestContig.GC * weight + curCore.GC * (1.0 - weight)
+                curCore.coverage = closestContig.coverage * weight + curCore.coverage * (1.0 - weight)
+                for i in range(0, len(curCore.tetraSig)):
+                    curCore.tetraSig[i] = closestContig.tetraSig[i] * weight + curCore.tetraSig[i] * (1.0 - weight)
+            else:
+                bCoreExpanded = False
+                if curCore.length > minBinSize:
+                    numCores += 1
+                    curCore.contigs = contigsInCurCore
+                    cores.append(curCore)
+                else:
+                    for contig in contigsInCurCore:
+                        contig.bProcessed = False
+                        contig.binId = -1
+    return cores

@@ -157,3 +157,39 @@ def test_split_and_base_count_oracle_matches_reference_outputs():
     for s, want in zip(seqs, g['baseCount']):
         assert list(O.base_count_literal(s)) == want
     assert any(v == [0, 0] for c in g['splits'] for v in c['contigs'].values())      # the empty leading contig quirk
+
+
+class _GContig(object):
+    def __init__(self, length, GC, coverage, tetraSig):
+        self.binId = -1
+        self.length, self.GC, self.coverage, self.tetraSig = length, GC, coverage, tetraSig
+
+
+def greedy_case(tag):
+    """Inputs and the reference's own outputs of one golden greedy case (tests/golden/make_golden_greedy.py)."""
+    import ast
+    from dbb_b200 import synthetic
+    from dbb_b200.data import load_td_dist
+    g = util.golden_npz('ref_greedy.npz')
+    contigs = [_GContig(int(l), float(a), float(b), s.copy()) for l, a, b, s in
+               zip(g[tag + '_length'], g[tag + '_gc'], g[tag + '_cov'], g[tag + '_sig'])]
+    td = load_td_dist()
+    return g, contigs, int(g[tag + '_params'][0]), int(g[tag + '_params'][1]), synthetic.synthetic_gc_dist(sorted(td.keys())), td, \
+        synthetic.synthetic_cov_dist(seed=7)
+
+
+def check_greedy_against_golden(g, tag, contigs, cores):
+    assert np.array_equal(np.array([c.binId for c in contigs]), g[tag + '_binId'])
+    assert len(cores) == len(g[tag + '_core_len'])
+    for b, core in enumerate(cores):
+        assert core.length == g[tag + '_core_len'][b] and core.GC == g[tag + '_core_gc'][b] and core.coverage == g[tag + '_core_cov'][b]
+        assert np.array_equal(np.asarray(core.tetraSig), g[tag + '_core_sig'][b])        # same float64 operations, same order
+        assert len(core.contigs) == g[tag + '_core_sizes'][b]
+
+
+def test_greedy_oracle_matches_reference_outputs():
+    """N3 row: the literal restatement of greedy.py:172-251 reproduces what the reference's own __greedy produced."""
+    for tag in ('a', 'b'):
+        g, contigs, per, minBin, gcDist, tdDist, covDist = greedy_case(tag)
+        cores = O.greedy_literal(contigs, minBin, O.Distributions(gcDist, per, tdDist, per, covDist, per))
+        check_greedy_against_golden(g, tag, contigs, cores)
