@@ -81,6 +81,8 @@ SIGNATURES = {
     'dbb_refine_dev': (ctypes.c_int, [ctypes.POINTER(RefineInput), ctypes.POINTER(RefineOutput), c_vp]),
     'dbb_refine_host': (ctypes.c_int, [ctypes.POINTER(RefineInput), ctypes.POINTER(RefineOutput)]),
     'dbb_greedy_host': (ctypes.c_int, [ctypes.POINTER(GreedyInput), c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'dbb_pca_gram_host': (ctypes.c_int, [c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp]),
+    'dbb_pca_project_host': (ctypes.c_int, [c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_i32, c_vp]),
     'dbb_pad_signatures_dev': (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp]),
     'dbb_synth_ascii_dev': (ctypes.c_int, [ctypes.c_uint64, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp,
                                            c_vp, c_vp, c_vp]),

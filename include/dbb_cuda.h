@@ -236,6 +236,15 @@ typedef struct {
 int dbb_greedy_host(const dbb_greedy_input* in_host, int64_t min_bin_size, int32_t* bin_id, int64_t* n_cores,
                     int64_t* core_len, double* core_gc, double* core_cov, double* core_sig, int64_t* n_steps);
 
+/* ---- "next" row N4: PCA of the signature matrix -- PCA.pcaMatrix, pca.py:56-75, with Center, pca.py:113-126 ----
+ * dbb_pca_gram_host: mean[w] = A.mean(0); std[w] = population std of the centred columns if scale != 0 (0 -> 1,
+ * pca.py:121-122) else ones; gram[w][w] = X^T X of X = (A - mean) / std, all FP64.  The caller solves the w x w
+ * symmetric eigenproblem (singular values d = sqrt(eigenvalues), rows of Vt = eigenvectors) and gets the scores
+ * pc() = X . V[:, :npc] from dbb_pca_project_host (V column-major-by-component: V[c][k], [w][npc]). */
+int dbb_pca_gram_host(const double* A, int64_t n, int32_t w, int32_t scale, double* mean, double* std_out, double* gram);
+int dbb_pca_project_host(const double* A, int64_t n, int32_t w, const double* mean, const double* std_in, const double* V,
+                         int32_t npc, double* scores);
+
 #ifdef __cplusplus
 }
 #endif
