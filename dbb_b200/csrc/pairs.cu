@@ -90,6 +90,11 @@ struct Params {
   uint32_t* item_counter;
   unsigned long long* stats;   // profiling builds only (-DDBB_K2_STATS, run with DBB_K2_STATS=1): [0] queued pairs, [1] drains, [2] top-k candidates
   int32_t* part_idx; float* part_dist; int32_t* part_cnt; int64_t* part_bp;
+  // optional sparse sweep (all NULL = every row tile visits column tiles 0..n_ct-1 in order):
+  const int32_t* item_order;   // [n_rt] row tile handled by work position p (whole sweeps first, then the split ones)
+  const int64_t* tile_off;     // [n_rt + 1] offsets into tile_list, indexed by row tile
+  const int32_t* tile_list;    // column tiles each row tile visits, ascending
+  const int32_t* col_id;       // [n] the caller's id of column j (tie-breaks and knn_idx use it instead of j)
 };
 
 struct SmemLayout {
@@ -105,7 +110,7 @@ struct SmemLayout {
   int32_t cnt[TILE];                     // neighbourhood size per row
   float thr[TILE];                       // current k-th best distance per row (+inf until k found)
   int32_t qn[MAX_WARPS];                 // queue fill per warp
-  ColScalars cols[2];                    // column scalars of tile ct live in cols[ct & 1]
+  ColScalars cols[2];                    // column scalars of the t-th visited tile live in cols[t & 1]
   alignas(8) uint64_t full[NSTAGE];
   uint64_t empty[NSTAGE];
   uint64_t a_full;
@@ -278,7 +283,9 @@ __device__ __noinline__ void process_row_pair(const Params& P, int par, int warp
         const int crow = lr0 + (src >> 4);
         const float cd = __shfl_sync(0xffffffffu, d, src);
         if (cd <= sm.thr[crow]) {            // the list may have tightened since the ballot
-          const float nt = list_insert(sm, crow, cd, (int32_t)(col_base + (src & 15) + 16 * j), k, lane);
+          int32_t cc = (int32_t)(col_base + (src & 15) + 16 * j);
+          if (P.col_id) cc = __ldg(P.col_id + cc);
+          const float nt = list_insert(sm, crow, cd, cc, k, lane);
           if (lane == 0) sm.thr[crow] = nt;
         }
         __syncwarp();
@@ -429,7 +436,8 @@ __device__ __noinline__ void drain_queue(const Params& P, int par, int warp, int
         m &= m - 1;
         const int crow = __shfl_sync(0xffffffffu, lr, src);
         const float cd = __shfl_sync(0xffffffffu, d, src);
-        const int32_t cc = (int32_t)__shfl_sync(0xffffffffu, (int)cj, src);
+        int32_t cc = (int32_t)__shfl_sync(0xffffffffu, (int)cj, src);
+        if (P.col_id) cc = __ldg(P.col_id + cc);
         if (cd <= sm.thr[crow]) {          // the list may have tightened since the candidate was flagged
           const float nt = list_insert(sm, crow, cd, cc, k, lane);
           if (lane == 0) sm.thr[crow] = nt;
@@ -505,7 +513,7 @@ __device__ __noinline__ void test_row_pair(int par, int warp, int lane, int i, i
 // belongs to tile ctile-1 because NSTAGE <= NKC, has been consumed by every warp) implies those are over.
 // (Inlined: an out-of-line call was 1.5 % slower, profiles/r01_pairs_notes.md.)
 template <int FLAGS>
-__device__ __forceinline__ void issue_chunk(const CUtensorMap* tmap, const Params& P, uint32_t qg, int ctile, int kc) {
+__device__ __forceinline__ void issue_chunk(const CUtensorMap* tmap, const Params& P, uint32_t qg, int ctile, int kc, int par) {
   constexpr bool F_TD = (FLAGS & 1) != 0, F_GCCOV = (FLAGS & 2) != 0;
   SmemLayout& sm = smem();
   const bool has_gc = F_GCCOV && P.gc != nullptr, has_cov = F_GCCOV && P.cov != nullptr;
@@ -518,7 +526,7 @@ __device__ __forceinline__ void issue_chunk(const CUtensorMap* tmap, const Param
     tma_load_2d(&sm.b[st][0][0], tmap, kc * KCH, ctile * TILE, bar);
     return;
   }
-  ColScalars& cs = sm.cols[ctile & 1];
+  ColScalars& cs = sm.cols[par];
   const int64_t c0 = (int64_t)ctile * TILE;
   if (c0 + TILE <= n) {
     // full column tile: fixed sizes, no tails
@@ -603,25 +611,32 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pairs_kernel(const __grid_const
     __syncthreads();
     const int item = sm.item;
     if (item >= P.n_items) break;
-    int rt, seg = -1, ct0 = 0, ct1 = n_ct;
-    if (item < P.n_full_rt) {
-      rt = item;
-    } else {
+    // work position -> row tile, segment of its tile sequence [t0, t1)
+    int pos = item, seg = -1, srt = 0;
+    if (item >= P.n_full_rt) {
       const int t = item - P.n_full_rt;
-      rt = P.n_full_rt + t / P.n_seg;
+      srt = t / P.n_seg;                   // index among the split row tiles (slot of the partial results)
+      pos = P.n_full_rt + srt;
       seg = t % P.n_seg;
-      ct0 = (int)(((int64_t)n_ct * seg) / P.n_seg);
-      ct1 = (int)(((int64_t)n_ct * (seg + 1)) / P.n_seg);
     }
+    const int rt = P.item_order ? __ldg(P.item_order + pos) : pos;
+    const int64_t list_base = P.tile_off ? __ldg(P.tile_off + rt) : 0;
+    const int n_tiles = P.tile_off ? (int)(__ldg(P.tile_off + rt + 1) - list_base) : n_ct;
+    const int t0 = seg < 0 ? 0 : (int)(((int64_t)n_tiles * seg) / P.n_seg);
+    const int t1 = seg < 0 ? n_tiles : (int)(((int64_t)n_tiles * (seg + 1)) / P.n_seg);
+    auto tile_at = [&](int t) -> int { return P.tile_list ? __ldg(P.tile_list + list_base + t) : t; };
     const int64_t row_base = P.row0 + (int64_t)rt * TILE;
-    const uint32_t item_chunks = (uint32_t)(ct1 - ct0) * NKC;
+    const uint32_t item_chunks = (uint32_t)(t1 - t0) * NKC;
     const uint32_t qbase = q;
 
     // thread 0 doubles as the TMA producer: A tile of this item + its first PREFETCH B chunks
     if (tid == 0) {
       mbar_arrive_expect_tx(&sm.a_full, NKC * CHUNK_BYTES);
       for (int kc = 0; kc < NKC; ++kc) tma_load_2d(&sm.a[kc][0][0], &tmap, kc * KCH, (int32_t)row_base, &sm.a_full);
-      for (uint32_t l = 0; l < (uint32_t)PREFETCH && l < item_chunks; ++l) issue_chunk<FLAGS>(&tmap, P, qbase + l, ct0 + (int)(l / NKC), (int)(l % NKC));
+      for (uint32_t l = 0; l < (uint32_t)PREFETCH && l < item_chunks; ++l) {
+        const int ts = t0 + (int)(l / NKC);
+        issue_chunk<FLAGS>(&tmap, P, qbase + l, tile_at(ts), (int)(l % NKC), ts & 1);
+      }
     }
     // stage row scalars and reset the per-row state of this warp's 16 rows
     if (lane < RW) {
@@ -659,7 +674,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pairs_kernel(const __grid_const
 #else
 #define DBB_LAP(var)
 #endif
-    for (int ct = ct0; ct < ct1; ++ct) {
+    for (int ts = t0; ts < t1; ++ts) {
+      const int ct = tile_at(ts);
       float2 acc[RI][8];
       #pragma unroll
       for (int i = 0; i < RI; ++i)
@@ -671,7 +687,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pairs_kernel(const __grid_const
         const uint32_t st = q % NSTAGE;
         if (tid == 0 && l + PREFETCH < item_chunks) {
           const uint32_t ln = l + PREFETCH;
-          issue_chunk<FLAGS>(&tmap, P, qbase + ln, ct0 + (int)(ln / NKC), (int)(ln % NKC));
+          const int tn = t0 + (int)(ln / NKC);
+          issue_chunk<FLAGS>(&tmap, P, qbase + ln, tile_at(tn), (int)(ln % NKC), tn & 1);
         }
         mbar_wait(&sm.full[st], (q / NSTAGE) & 1);
         const float* bq = &sm.b[st][tx][0];
@@ -714,7 +731,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pairs_kernel(const __grid_const
       DBB_LAP(t_main)
       // ---------------- epilogue of this column tile ----------------
       const int64_t col_base = (int64_t)ct * TILE;
-      const ColScalars& cs = sm.cols[ct & 1];
+      const ColScalars& cs = sm.cols[ts & 1];
       if (P.debug_skip_epilogue == 1) {
         float keep = 0.f;
         #pragma unroll
@@ -729,25 +746,28 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pairs_kernel(const __grid_const
           #pragma unroll
           for (int j = 0; j < 8; ++j) sm.q[warp * QCAP + (j * 32 + lane)].x = fin(acc[i][j]);
           __syncwarp();
-          process_row_pair<FLAGS, WARPS>(P, ct & 1, warp, lane, warp * RW + 2 * i, row_base, col_base);
+          process_row_pair<FLAGS, WARPS>(P, ts & 1, warp, lane, warp * RW + 2 * i, row_base, col_base);
         }
       } else {
         // steady state: one out-of-line call per row pair (see test_row_pair); a row pair pushes at most 256
         // entries, so checking the fill after every second one needs 512 free slots
         if (lane == 0) sm.qn[warp] = 0;
         __syncwarp();
-        const int tflags = ((F_TOPK && ct == ct0) ? 1 : 0) | (want_cnt ? 2 : 0);
+        // (the first-tile threshold assumes that any column may enter the list: not with a filtered top-k, where the
+        // columns below it may all fail the filter -- then the first tile is taken whole, like any tile before the
+        // list is full)
+        const int tflags = ((F_TOPK && ts == t0 && P.topk_filter == 0) ? 1 : 0) | (want_cnt ? 2 : 0);
         const int ncol = (int)((n - col_base) < (int64_t)TILE ? (n - col_base) : (int64_t)TILE);
         #pragma unroll
         for (int i = 0; i < RI; ++i) {
-          test_row_pair<FLAGS, WARPS>(ct & 1, warp, lane, i, tflags, ncol, P.k,
+          test_row_pair<FLAGS, WARPS>(ts & 1, warp, lane, i, tflags, ncol, P.k,
                                       fin(acc[i][0]), fin(acc[i][1]), fin(acc[i][2]), fin(acc[i][3]), fin(acc[i][4]),
                                       fin(acc[i][5]), fin(acc[i][6]), fin(acc[i][7]));
           if ((i & 1) && i + 1 < RI) {
             __syncwarp();
             const int qn = sm.qn[warp];
             if (qn > QCAP - 512) {
-              drain_queue<FLAGS, WARPS>(P, ct & 1, warp, lane, qn, row_base, col_base);
+              drain_queue<FLAGS, WARPS>(P, ts & 1, warp, lane, qn, row_base, col_base);
               if (lane == 0) sm.qn[warp] = 0;
               __syncwarp();
             }
@@ -756,7 +776,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pairs_kernel(const __grid_const
         __syncwarp();
         const int qn = sm.qn[warp];
         DBB_LAP(t_test)
-        if (qn && P.debug_skip_epilogue != 2) drain_queue<FLAGS, WARPS>(P, ct & 1, warp, lane, qn, row_base, col_base);
+        if (qn && P.debug_skip_epilogue != 2) drain_queue<FLAGS, WARPS>(P, ts & 1, warp, lane, qn, row_base, col_base);
       }
       DBB_LAP(t_drain)
     }  // column tiles
@@ -780,7 +800,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pairs_kernel(const __grid_const
           if (P.count) P.count[gi - P.row0] = sm.cnt[lr];
           if (P.neighbour_bp) P.neighbour_bp[gi - P.row0] = bp;
         } else {
-          const int64_t o = ((int64_t)(rt - P.n_full_rt) * TILE + lr) * P.n_seg + seg;
+          const int64_t o = ((int64_t)srt * TILE + lr) * P.n_seg + seg;
           P.part_cnt[o] = sm.cnt[lr];
           P.part_bp[o] = bp;
         }
@@ -797,7 +817,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pairs_kernel(const __grid_const
             if (P.knn_idx) P.knn_idx[(gi - P.row0) * k + lane] = (ej == INT_MAX) ? -1 : ej;
             if (P.knn_dist) P.knn_dist[(gi - P.row0) * k + lane] = ed;
           } else {
-            const int64_t o = (((int64_t)(rt - P.n_full_rt) * TILE + lr) * P.n_seg + seg) * k + lane;
+            const int64_t o = (((int64_t)srt * TILE + lr) * P.n_seg + seg) * k + lane;
             P.part_idx[o] = ej;
             P.part_dist[o] = ed;
           }
@@ -810,11 +830,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pairs_kernel(const __grid_const
 
 // Merge of the partial results of split row tiles: one warp per row, lane l holds entry l of the sorted
 // list; the (distance, index) order is total, so the merged list is the same as an unsplit sweep's.
-__global__ void __launch_bounds__(128) merge_kernel(const Params P, int64_t first_row, int64_t n_split_rows) {
+__global__ void __launch_bounds__(128) merge_kernel(const Params P, int64_t n_split_rows) {
   const int lane = threadIdx.x & 31;
-  const int64_t r = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int64_t r = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);   // split row tile r / TILE, row r % TILE of it
   if (r >= n_split_rows) return;
-  const int64_t gi = first_row + r;             // row index relative to row0
+  const int pos = P.n_full_rt + (int)(r / TILE);
+  const int rt = P.item_order ? P.item_order[pos] : pos;
+  const int64_t gi = (int64_t)rt * TILE + (r % TILE);               // row index relative to row0
+  if (gi >= P.row1 - P.row0) return;
   const int k = P.k;
   int32_t cnt = 0;
   int64_t bp = 0;
@@ -957,6 +980,8 @@ DBB_EXPORT int dbb_pairs_dev(const dbb_pairs_input* in, int64_t row0, int64_t ro
   const bool masks = out->td_mask || out->gc_mask || out->cov_mask;
   DBB_REQUIRE(!masks || out->mask_words * 32 >= in->n, "mask_words too small");
   DBB_REQUIRE(!out->td_mask || in->td_bound, "td_mask requested without td_bound");
+  DBB_REQUIRE((in->tile_off == nullptr) == (in->tile_list == nullptr), "tile_off and tile_list go together");
+  DBB_REQUIRE(!in->tile_off || !masks, "masks need every column tile: not available with a sparse sweep (tile_off / tile_list)");
 
   EncodeTiledFn encode;
   int rc = get_encode_fn(&encode);
@@ -977,6 +1002,7 @@ DBB_EXPORT int dbb_pairs_dev(const dbb_pairs_input* in, int64_t row0, int64_t ro
   P.gc = in->gc; P.gc_mbin = in->gc_mbin; P.gc_lbin = in->gc_lbin; P.gc_lo = in->gc_lo; P.gc_hi = in->gc_hi; P.gc_nl = in->gc_nl;
   P.cov = in->cov; P.cov_lbin = in->cov_lbin; P.cov_lo = in->cov_lo; P.cov_hi = in->cov_hi;
   P.k = out->k; P.topk_filter = out->topk_filter;
+  P.col_id = in->col_id; P.item_order = in->item_order; P.tile_off = in->tile_off; P.tile_list = in->tile_list;
   P.knn_idx = out->knn_idx; P.knn_dist = out->knn_dist; P.count = out->count; P.neighbour_bp = out->neighbour_bp;
   P.td_mask = out->td_mask; P.gc_mask = out->gc_mask; P.cov_mask = out->cov_mask; P.mask_words = out->mask_words;
 
@@ -997,7 +1023,7 @@ DBB_EXPORT int dbb_pairs_dev(const dbb_pairs_input* in, int64_t row0, int64_t ro
   P.n_items = (int32_t)(n_full + rem * n_seg);
   P.opaque_zero = 0;
   { const char* e2 = getenv("DBB_K2_DEBUG_SKIP_EPILOGUE"); P.debug_skip_epilogue = (e2 && *e2) ? atoi(e2) : 0; }   // profiling only
-  const int64_t split_rows = std::min<int64_t>(rem * TILE, n_rows - n_full * TILE);
+  const int64_t split_rows = rem * TILE;          // merge_kernel skips the rows of a last, partial row tile itself
   const size_t k_ = (size_t)std::max(out->k, 1);
   size_t off_idx = 256, off_dist, off_cnt, off_bp, total;
   off_dist = off_idx + (size_t)rem * TILE * n_seg * k_ * 4;
@@ -1031,7 +1057,7 @@ DBB_EXPORT int dbb_pairs_dev(const dbb_pairs_input* in, int64_t row0, int64_t ro
   if (in->metric == DBB_METRIC_L2) flags |= 16;
   rc = launch_pairs(flags, grid, smem, st, tmap, P);
   if (rc == DBB_OK && rem > 0 && split_rows > 0) {
-    merge_kernel<<<(unsigned)((split_rows + 3) / 4), 128, 0, st>>>(P, n_full * TILE, split_rows);
+    merge_kernel<<<(unsigned)((split_rows + 3) / 4), 128, 0, st>>>(P, split_rows);
     if (cudaGetLastError() != cudaSuccess) { dbb::set_error("merge kernel launch failed"); rc = DBB_ERR_CUDA; }
   }
   if (want_stats && rc == DBB_OK) {

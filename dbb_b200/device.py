@@ -141,9 +141,11 @@ def pad_signatures(dense):
     return out
 
 
-def pairs(sig_padded, dt, row0=0, row1=None, k=0, topk_filter=0, want_count=True, masks=(), metric='l1'):
+def pairs(sig_padded, dt, row0=0, row1=None, k=0, topk_filter=0, want_count=True, masks=(), metric='l1', sparse=None):
     """Rows [row0,row1) of the all-pairs problem on the current device/stream.
-    sig_padded: float32 cuda [N,140]; dt: DevicePairTables.  Returns a dict of cuda tensors."""
+    sig_padded: float32 cuda [N,140]; dt: DevicePairTables.  Returns a dict of cuda tensors.
+    sparse: optional (col_id int32[N], item_order int32[row tiles], tile_off int64[row tiles + 1], tile_list int32[...])
+    cuda tensors -- the sparse sweep of include/dbb_cuda.h (see pairs_pruned)."""
     require_cuda()
     n = dt.n
     row1 = n if row1 is None else row1
@@ -154,6 +156,8 @@ def pairs(sig_padded, dt, row0=0, row1=None, k=0, topk_filter=0, want_count=True
     inp.n = n
     inp.sig, inp.length, inp.td_bound = _p(sig_padded), _p(dt.length), _p(dt.td_bound)
     inp.metric = _lib.METRICS[metric]
+    if sparse is not None:
+        inp.col_id, inp.item_order, inp.tile_off, inp.tile_list = (_p(t) for t in sparse)
     if dt.gc is not None:
         inp.gc, inp.gc_mbin, inp.gc_lbin, inp.gc_lo, inp.gc_hi = _p(dt.gc), _p(dt.gc_mbin), _p(dt.gc_lbin), _p(dt.gc_lo), _p(dt.gc_hi)
         inp.gc_nm, inp.gc_nl = dt.gc_lo.shape
@@ -179,6 +183,125 @@ def pairs(sig_padded, dt, row0=0, row1=None, k=0, topk_filter=0, want_count=True
     if rows and n:
         _lib.check(_lib.lib().dbb_pairs_dev(ctypes.byref(inp), row0, row1, ctypes.byref(out), _stream()))
     return res
+
+
+_GC_WEIGHTS = None
+
+
+def projection_weights(device):
+    """float32[140]: GC fraction of every canonical tetramer (0, .25, .5, .75, 1), zero for the padding columns.
+    Any weights in [0, 1] give the bound used by pairs_pruned; these spread metagenomes by their GC content."""
+    global _GC_WEIGHTS
+    if _GC_WEIGHTS is None:
+        names, _ = _lib.kmer_table()
+        w = np.zeros(_lib.SIG_STRIDE, dtype=np.float32)
+        w[:_lib.NUM_KMERS] = [sum(ch in 'GC' for ch in nm) / 4.0 for nm in names]
+        _GC_WEIGHTS = w
+    return torch.from_numpy(_GC_WEIGHTS).to(device)
+
+
+class _SortedTables(object):
+    pass
+
+
+def pairs_pruned(sig_padded, dt, row0=0, row1=None, k=0, topk_filter=0, want_count=True, metric='l1', margin=1e-5):
+    """Same results as ``pairs`` (no masks), skipping 128 x 128 tiles of the pair matrix that cannot matter.
+
+    Signatures sum to 1, so for ANY weights w_k in [0, 1] and p = sum_k w_k sig_k:  L1(a, b) >= 2 |p_a - p_b|
+    (sum_k (w_k - 1/2)(a_k - b_k) equals p_a - p_b and is at most L1 / 2 in magnitude).  With the scaffolds sorted by p
+    every tile has a p interval; a tile pair whose intervals are farther apart than half the largest TD bound of its
+    rows and columns holds no TD neighbour (the bound of a pair is the bound of its shorter scaffold), hence nothing
+    that counts and no candidate of a TD-filtered top-k.  For an unfiltered top-k a second launch visits the tiles whose
+    lower bound does not exceed the k-th best distance found so far of some row of the row tile, and the lists are
+    merged; results are identical to the unpruned sweep, ties included (lists are ordered by (distance, original id)).
+    [row0, row1) are positions in the p-sorted order (multi-GPU: equal blocks of it); the dict carries ``row_ids``,
+    the original ids of the returned rows, and ``tiles_visited`` / ``tiles_total``.  Planning (projection, sort,
+    gathers, tile mask) uses torch ops on the device; the distance work is the same pairs_kernel."""
+    require_cuda()
+    if metric != 'l1':
+        raise ValueError('pairs_pruned: the projection bound is for the Manhattan distance')
+    if want_count and dt.td_bound is None:
+        raise ValueError('pairs_pruned: without a TD bound every pair may count, nothing can be skipped (use pairs)')
+    n = dt.n
+    row1 = n if row1 is None else row1
+    dev = sig_padded.device
+    T = 128
+    p = torch.mv(sig_padded, projection_weights(dev))
+    p_s, perm = torch.sort(p, stable=True)
+    sig_s = sig_padded.index_select(0, perm)
+    st = _SortedTables()
+    st.n = n
+    for name in ('length', 'td_bound', 'gc', 'gc_mbin', 'gc_lbin', 'cov', 'cov_lbin'):
+        a = getattr(dt, name)
+        setattr(st, name, None if a is None else a.index_select(0, perm))
+    st.gc_lo, st.gc_hi, st.cov_lo, st.cov_hi = dt.gc_lo, dt.gc_hi, dt.cov_lo, dt.cov_hi
+    n_ct = (n + T - 1) // T
+    n_rt = (row1 - row0 + T - 1) // T
+    pad = n_ct * T - n
+    p_pad = torch.cat([p_s, p_s[-1:].expand(pad)]) if pad else p_s
+    pmin_c, pmax_c = p_pad[0::T], p_pad[T - 1::T]
+    r_first = row0 + T * torch.arange(n_rt, device=dev)
+    r_last = torch.clamp(r_first + (T - 1), max=row1 - 1)
+    pmin_r, pmax_r = p_s[r_first], p_s[r_last]
+    gap = torch.maximum(pmin_c[None, :] - pmax_r[:, None], pmin_r[:, None] - pmax_c[None, :]).clamp_(min=0)
+    lb = 2.0 * gap - margin                                   # lower bound of every distance in the tile pair
+    if st.td_bound is not None:
+        tdb_pad = torch.cat([st.td_bound, st.td_bound.new_full((pad,), float('-inf'))]) if pad else st.td_bound
+        tmax_c = tdb_pad.view(n_ct, T).amax(1)
+        rows_pad = n_rt * T - (row1 - row0)
+        tdb_rows = st.td_bound[row0:row1]
+        if rows_pad:
+            tdb_rows = torch.cat([tdb_rows, tdb_rows.new_full((rows_pad,), float('-inf'))])
+        tmax_r = tdb_rows.view(n_rt, T).amax(1)
+        need = lb <= torch.maximum(tmax_r[:, None], tmax_c[None, :])
+    else:
+        need = lb <= 0
+    col_id = perm.to(torch.int32)
+
+    def lists(mask):
+        cnt = mask.sum(1)
+        off = torch.zeros(n_rt + 1, dtype=torch.int64, device=dev)
+        off[1:] = torch.cumsum(cnt, 0)
+        tl = torch.nonzero(mask)[:, 1].to(torch.int32).contiguous()
+        order = torch.argsort(cnt, descending=True, stable=True).to(torch.int32)
+        return (col_id, order, off, tl), int(off[-1].item())
+
+    sp, visited = lists(need)
+    res = pairs(sig_s, st, row0, row1, k=k, topk_filter=topk_filter, want_count=want_count, metric=metric, sparse=sp)
+    if k > 0 and not (topk_filter & FILTER_TD):
+        # unfiltered (or GC / coverage filtered) top-k: candidates may sit beyond the TD window
+        thr = res['dist'][:, k - 1]
+        rows_pad = n_rt * T - (row1 - row0)
+        if rows_pad:
+            thr = torch.cat([thr, thr.new_full((rows_pad,), float('-inf'))])
+        t_r = thr.view(n_rt, T).amax(1)
+        more = (lb <= t_r[:, None]) & ~need
+        if bool(more.any().item()):
+            sp2, v2 = lists(more)
+            visited += v2
+            r2 = pairs(sig_s, st, row0, row1, k=k, topk_filter=topk_filter, want_count=False, metric=metric, sparse=sp2)
+            d = torch.cat([res['dist'], r2['dist']], 1)
+            j = torch.cat([res['idx'], r2['idx']], 1)
+            jkey = torch.where(j < 0, torch.full_like(j, 2 ** 31 - 1), j)
+            o1 = torch.argsort(jkey, dim=1, stable=True)
+            d, j = d.gather(1, o1), j.gather(1, o1)
+            o2 = torch.argsort(d, dim=1, stable=True)[:, :k]
+            res['dist'], res['idx'] = d.gather(1, o2).contiguous(), j.gather(1, o2).contiguous()
+    res['row_ids'] = perm[row0:row1]
+    res['tiles_visited'], res['tiles_total'] = visited, n_rt * n_ct
+    return res
+
+
+def unsort_rows(res, n):
+    """Results of a full-range pairs_pruned call back in the caller's row order."""
+    out = {}
+    ids = res['row_ids']
+    for key in ('idx', 'dist', 'count', 'neighbour_bp'):
+        if key in res:
+            t = torch.empty_like(res[key])
+            t[ids] = res[key]
+            out[key] = t
+    return out
 
 
 # ------------------------------------------------------------------------------------------------

@@ -142,6 +142,18 @@ typedef struct {
    * by the same shorter-scaffold rule; GC / coverage predicates and masks are not available with it).
    * Both run on the FP32 CUDA cores; tolerance 2e-6 absolute against FP64 (tests/test_pairs_gpu.py). */
   int32_t metric;
+  /* Optional sparse sweep, dbb_pairs_dev only (all NULL = every row visits every column).  The caller may know that
+   * whole 128 x 128 tiles of the pair matrix cannot hold a neighbour or a top-k candidate -- e.g. with the scaffolds
+   * sorted by a projection p = sum_k w_k sig_k, w_k in [0, 1], L1(a, b) >= 2 |p_a - p_b| because signatures sum
+   * to 1 (dbb_b200/device.py::pairs_pruned builds exactly that) -- and passes, for row tile t of [row0, row1)
+   * (rows row0 + 128 t ...), the ascending list of column tiles it must visit: tile_list[tile_off[t] .. tile_off[t+1]).
+   * item_order[n_row_tiles]: a permutation of the row tiles, most work first (scheduling only).  col_id[n]: the
+   * caller's own id of column j, used instead of j for the (distance, id) order of the top-k lists and in knn_idx,
+   * so that results do not depend on how the caller sorted the scaffolds.  Masks cannot be requested with tile lists. */
+  const int32_t* col_id;
+  const int32_t* item_order;
+  const int64_t* tile_off;
+  const int32_t* tile_list;
 } dbb_pairs_input;
 
 typedef struct {

@@ -267,3 +267,48 @@ def test_euclidean_metric_knn_and_bounded_count():
         _pairs.run_pairs_host(sig64, PairTables(meta.length, GC=meta.gc_obs, gcDist=_dists()[1], gcDistPer=80), k=20, metric='l2')
     with pytest.raises(ValueError):
         _pairs.run_pairs_host(sig64, tables, k=20, metric='cosine')
+
+
+def test_pruned_sweep_equals_full_sweep():
+    """device.pairs_pruned (sorted by a projection, tiles that cannot matter skipped, second launch for unfiltered
+    top-k) returns exactly what the full sweep returns: indices, distances bit for bit, counts, base pairs."""
+    import torch
+    from dbb_b200 import device, synthetic
+    from dbb_b200.distributions import PairTables
+    from dbb_b200.genomicSignatures import GenomicSignatures
+    meta = synthetic.make_metagenome(seed=51, n_scaffolds=2600, min_len=1000, max_len=60000, n_genomes=12)
+    seqs = synthetic.generate_sequences(meta)
+    _, freq = GenomicSignatures(4, 1).signatures(seqs)
+    freq[100] = freq[101]                                               # exact distance ties: order by original id
+    freq[2000] = freq[101]
+    sig = device.pad_signatures(torch.from_numpy(freq).cuda())
+    td, gcd, cvd = _dists()
+    n = meta.n_scaffolds
+    cases = [
+        (PairTables(meta.length, tdDist=td, tdDistPer=80), 0),
+        (PairTables(meta.length, tdDist=td, tdDistPer=80), device.FILTER_TD),
+        (PairTables(meta.length, GC=meta.gc_obs, coverage=meta.coverage, tdDist=td, tdDistPer=80, gcDist=gcd, gcDistPer=80,
+                    covDist=cvd, covDistPer=80), device.FILTER_GC | device.FILTER_COV),
+        (PairTables(meta.length), 0),                                   # no bound at all: plain k-NN
+    ]
+    skipped = []
+    for tables, filt in cases:
+        dt = device.DevicePairTables(tables)
+        cnt = tables.td_bound is not None                              # without a bound every pair counts: nothing to skip
+        full = device.pairs(sig, dt, k=20, topk_filter=filt, want_count=cnt)
+        pr = device.pairs_pruned(sig, dt, k=20, topk_filter=filt, want_count=cnt)
+        got = device.unsort_rows(pr, n)
+        for key in ('idx', 'dist') + (('count', 'neighbour_bp') if cnt else ()):
+            assert torch.equal(got[key], full[key]), (key, filt)
+        skipped.append(1.0 - pr['tiles_visited'] / pr['tiles_total'])
+    assert skipped[1] > 0.05                                           # the TD-filtered case really skips tiles
+    with pytest.raises(ValueError):
+        device.pairs_pruned(sig, device.DevicePairTables(cases[3][0]), k=20, want_count=True)
+    # row blocks of the sorted order (what each GPU takes): together they are the full result
+    dt = device.DevicePairTables(cases[0][0])
+    full = device.pairs(sig, dt, k=20, want_count=True)
+    for r0, r1 in ((0, 900), (900, 1700), (1700, n)):
+        part = device.pairs_pruned(sig, dt, r0, r1, k=20, want_count=True)
+        ids = part['row_ids']
+        for key in ('idx', 'dist', 'count', 'neighbour_bp'):
+            assert torch.equal(part[key], full[key][ids]), (key, r0)
