@@ -27,7 +27,8 @@ class PairsInput(ctypes.Structure):
                 ('gc', c_vp), ('gc_mbin', c_vp), ('gc_lbin', c_vp), ('gc_lo', c_vp), ('gc_hi', c_vp),
                 ('gc_nm', c_i32), ('gc_nl', c_i32),
                 ('cov', c_vp), ('cov_lbin', c_vp), ('cov_lo', c_vp), ('cov_hi', c_vp), ('cov_nl', c_i32),
-                ('metric', c_i32), ('col_id', c_vp), ('item_order', c_vp), ('tile_off', c_vp), ('tile_list', c_vp)]
+                ('metric', c_i32), ('col_id', c_vp), ('item_order', c_vp), ('tile_off', c_vp), ('tile_list', c_vp),
+                ('split_all', c_i32), ('n_active_row_tiles', c_i32)]
 
 
 METRICS = {'l1': 0, 'manhattan': 0, 'l2': 1, 'euclidean': 1}

@@ -622,9 +622,15 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pairs_kernel(const __grid_const
     const int rt = P.item_order ? __ldg(P.item_order + pos) : pos;
     const int64_t list_base = P.tile_off ? __ldg(P.tile_off + rt) : 0;
     const int n_tiles = P.tile_off ? (int)(__ldg(P.tile_off + rt + 1) - list_base) : n_ct;
-    const int t0 = seg < 0 ? 0 : (int)(((int64_t)n_tiles * seg) / P.n_seg);
-    const int t1 = seg < 0 ? n_tiles : (int)(((int64_t)n_tiles * (seg + 1)) / P.n_seg);
-    auto tile_at = [&](int t) -> int { return P.tile_list ? __ldg(P.tile_list + list_base + t) : t; };
+    // a segment of a full sweep is a contiguous range of column tiles; a segment of a tile list takes every
+    // n_seg-th entry (the lists come nearest-first: every segment then sees near tiles early and its top-k
+    // threshold tightens at once)
+    const bool strided = P.tile_list != nullptr && seg >= 0;
+    const int t0 = (seg < 0 || strided) ? 0 : (int)(((int64_t)n_tiles * seg) / P.n_seg);
+    const int t1 = seg < 0 ? n_tiles : (strided ? (n_tiles - seg + P.n_seg - 1) / P.n_seg : (int)(((int64_t)n_tiles * (seg + 1)) / P.n_seg));
+    auto tile_at = [&](int t) -> int {
+      return P.tile_list ? __ldg(P.tile_list + list_base + (strided ? seg + t * P.n_seg : t)) : t;
+    };
     const int64_t row_base = P.row0 + (int64_t)rt * TILE;
     const uint32_t item_chunks = (uint32_t)(t1 - t0) * NKC;
     const uint32_t qbase = q;
@@ -982,6 +988,8 @@ DBB_EXPORT int dbb_pairs_dev(const dbb_pairs_input* in, int64_t row0, int64_t ro
   DBB_REQUIRE(!out->td_mask || in->td_bound, "td_mask requested without td_bound");
   DBB_REQUIRE((in->tile_off == nullptr) == (in->tile_list == nullptr), "tile_off and tile_list go together");
   DBB_REQUIRE(!in->tile_off || !masks, "masks need every column tile: not available with a sparse sweep (tile_off / tile_list)");
+  DBB_REQUIRE(in->split_all >= 0 && in->split_all <= 64 && in->n_active_row_tiles >= 0, "bad split_all / n_active_row_tiles");
+  DBB_REQUIRE(in->n_active_row_tiles == 0 || in->item_order, "n_active_row_tiles needs item_order");
 
   EncodeTiledFn encode;
   int rc = get_encode_fn(&encode);
@@ -1017,7 +1025,9 @@ DBB_EXPORT int dbb_pairs_dev(const dbb_pairs_input* in, int64_t row0, int64_t ro
 
   int64_t n_full, rem;
   int n_seg;
-  plan_items(n_rt, n_ct, sms, &n_full, &rem, &n_seg);
+  const int64_t n_rt_active = in->n_active_row_tiles > 0 ? std::min<int64_t>(in->n_active_row_tiles, n_rt) : n_rt;
+  if (in->split_all > 0) { n_full = 0; rem = n_rt_active; n_seg = in->split_all; }     // caller-planned sparse sweep
+  else plan_items(n_rt_active, n_ct, sms, &n_full, &rem, &n_seg);
   P.n_full_rt = (int32_t)n_full;
   P.n_seg = n_seg;
   P.n_items = (int32_t)(n_full + rem * n_seg);

@@ -144,8 +144,8 @@ def pad_signatures(dense):
 def pairs(sig_padded, dt, row0=0, row1=None, k=0, topk_filter=0, want_count=True, masks=(), metric='l1', sparse=None):
     """Rows [row0,row1) of the all-pairs problem on the current device/stream.
     sig_padded: float32 cuda [N,140]; dt: DevicePairTables.  Returns a dict of cuda tensors.
-    sparse: optional (col_id int32[N], item_order int32[row tiles], tile_off int64[row tiles + 1], tile_list int32[...])
-    cuda tensors -- the sparse sweep of include/dbb_cuda.h (see pairs_pruned)."""
+    sparse: optional (col_id int32[N], item_order int32[row tiles], tile_off int64[row tiles + 1], tile_list int32[...],
+    split_all, n_active_row_tiles) -- the sparse sweep of include/dbb_cuda.h (see pairs_pruned)."""
     require_cuda()
     n = dt.n
     row1 = n if row1 is None else row1
@@ -157,7 +157,8 @@ def pairs(sig_padded, dt, row0=0, row1=None, k=0, topk_filter=0, want_count=True
     inp.sig, inp.length, inp.td_bound = _p(sig_padded), _p(dt.length), _p(dt.td_bound)
     inp.metric = _lib.METRICS[metric]
     if sparse is not None:
-        inp.col_id, inp.item_order, inp.tile_off, inp.tile_list = (_p(t) for t in sparse)
+        inp.col_id, inp.item_order, inp.tile_off, inp.tile_list = (_p(t) for t in sparse[:4])
+        inp.split_all, inp.n_active_row_tiles = int(sparse[4]), int(sparse[5])
     if dt.gc is not None:
         inp.gc, inp.gc_mbin, inp.gc_lbin, inp.gc_lo, inp.gc_hi = _p(dt.gc), _p(dt.gc_mbin), _p(dt.gc_lbin), _p(dt.gc_lo), _p(dt.gc_hi)
         inp.gc_nm, inp.gc_nl = dt.gc_lo.shape
@@ -204,7 +205,8 @@ class _SortedTables(object):
     pass
 
 
-def pairs_pruned(sig_padded, dt, row0=0, row1=None, k=0, topk_filter=0, want_count=True, metric='l1', margin=1e-5):
+def pairs_pruned(sig_padded, dt, row0=0, row1=None, k=0, topk_filter=0, want_count=True, metric='l1', margin=1e-5,
+                 n_classes=8, timings=None):
     """Same results as ``pairs`` (no masks), skipping 128 x 128 tiles of the pair matrix that cannot matter.
 
     Signatures sum to 1, so for ANY weights w_k in [0, 1] and p = sum_k w_k sig_k:  L1(a, b) >= 2 |p_a - p_b|
@@ -214,7 +216,10 @@ def pairs_pruned(sig_padded, dt, row0=0, row1=None, k=0, topk_filter=0, want_cou
     that counts and no candidate of a TD-filtered top-k.  For an unfiltered top-k a second launch visits the tiles whose
     lower bound does not exceed the k-th best distance found so far of some row of the row tile, and the lists are
     merged; results are identical to the unpruned sweep, ties included (lists are ordered by (distance, original id)).
-    [row0, row1) are positions in the p-sorted order (multi-GPU: equal blocks of it); the dict carries ``row_ids``,
+    The sort key is (TD-bound class, p): the bound of a pair is the bound of its shorter scaffold, so tiles of long
+    scaffolds (small bounds) only need their near neighbours among each other; ``n_classes`` equal-count classes of the
+    per-scaffold bound keep the tiles homogeneous (any arrangement is exact, the intervals are taken per tile).
+    [row0, row1) are positions in the sorted order (multi-GPU: equal blocks of it); the dict carries ``row_ids``,
     the original ids of the returned rows, and ``tiles_visited`` / ``tiles_total``.  Planning (projection, sort,
     gathers, tile mask) uses torch ops on the device; the distance work is the same pairs_kernel."""
     require_cuda()
@@ -226,8 +231,27 @@ def pairs_pruned(sig_padded, dt, row0=0, row1=None, k=0, topk_filter=0, want_cou
     row1 = n if row1 is None else row1
     dev = sig_padded.device
     T = 128
+    marks = []
+
+    def mark(name):
+        if timings is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            marks.append((name, e))
+
+    mark('start')
     p = torch.mv(sig_padded, projection_weights(dev))
-    p_s, perm = torch.sort(p, stable=True)
+    key = p
+    if dt.td_bound is not None and n_classes > 1:
+        cls = getattr(dt, '_prune_class', None)
+        if cls is None or cls.shape[0] != n or getattr(dt, '_prune_nc', 0) != n_classes:
+            rank = torch.empty(n, dtype=torch.int64, device=dev)
+            rank[torch.argsort(dt.td_bound, stable=True)] = torch.arange(n, device=dev)
+            cls = ((rank * n_classes) // max(n, 1)).to(torch.float32)
+            dt._prune_class, dt._prune_nc = cls, n_classes
+        key = cls * 4.0 + p.clamp(0.0, 1.0)                        # p is in [0, 1]: classes do not interleave
+    perm = torch.argsort(key, stable=True)
+    p_s = p[perm]
     sig_s = sig_padded.index_select(0, perm)
     st = _SortedTables()
     st.n = n
@@ -239,10 +263,12 @@ def pairs_pruned(sig_padded, dt, row0=0, row1=None, k=0, topk_filter=0, want_cou
     n_rt = (row1 - row0 + T - 1) // T
     pad = n_ct * T - n
     p_pad = torch.cat([p_s, p_s[-1:].expand(pad)]) if pad else p_s
-    pmin_c, pmax_c = p_pad[0::T], p_pad[T - 1::T]
-    r_first = row0 + T * torch.arange(n_rt, device=dev)
-    r_last = torch.clamp(r_first + (T - 1), max=row1 - 1)
-    pmin_r, pmax_r = p_s[r_first], p_s[r_last]
+    pmin_c, pmax_c = p_pad.view(n_ct, T).amin(1), p_pad.view(n_ct, T).amax(1)
+    p_rows = p_s[row0:row1]
+    rows_pad0 = n_rt * T - (row1 - row0)
+    if rows_pad0:
+        p_rows = torch.cat([p_rows, p_rows[-1:].expand(rows_pad0)])
+    pmin_r, pmax_r = p_rows.view(n_rt, T).amin(1), p_rows.view(n_rt, T).amax(1)
     gap = torch.maximum(pmin_c[None, :] - pmax_r[:, None], pmin_r[:, None] - pmax_c[None, :]).clamp_(min=0)
     lb = 2.0 * gap - margin                                   # lower bound of every distance in the tile pair
     if st.td_bound is not None:
@@ -258,16 +284,28 @@ def pairs_pruned(sig_padded, dt, row0=0, row1=None, k=0, topk_filter=0, want_cou
         need = lb <= 0
     col_id = perm.to(torch.int32)
 
-    def lists(mask):
+    def lists(mask, active=None):
+        # every row tile visits its tiles nearest (smallest lower bound) first: the top-k threshold tightens at once
+        # and the far tiles add next to nothing (in ascending tile order every tile would bring better candidates
+        # than the one before -- the worst case for a streaming top-k)
         cnt = mask.sum(1)
         off = torch.zeros(n_rt + 1, dtype=torch.int64, device=dev)
         off[1:] = torch.cumsum(cnt, 0)
-        tl = torch.nonzero(mask)[:, 1].to(torch.int32).contiguous()
-        order = torch.argsort(cnt, descending=True, stable=True).to(torch.int32)
-        return (col_id, order, off, tl), int(off[-1].item())
+        key = torch.where(mask, lb, torch.full_like(lb, float('inf')))
+        by_lb = torch.argsort(key, dim=1, stable=True)
+        keep = torch.arange(n_ct, device=dev)[None, :] < cnt[:, None]
+        tl = by_lb[keep].to(torch.int32).contiguous()
+        order = torch.argsort(cnt, descending=True, stable=True).to(torch.int32)   # most work first; empty lists last
+        # ~10 work items per SM: the lists differ in length by an order of magnitude, whole row tiles do not balance
+        n_act = n_rt if active is None else active
+        split = int(min(8, max(1, -(-1480 // max(n_act, 1)))))
+        return (col_id, order, off, tl, split, 0 if active is None else active), int(off[-1].item())
 
     sp, visited = lists(need)
+    mark('plan')
     res = pairs(sig_s, st, row0, row1, k=k, topk_filter=topk_filter, want_count=want_count, metric=metric, sparse=sp)
+    mark('sweep')
+    visited1 = visited
     if k > 0 and not (topk_filter & FILTER_TD):
         # unfiltered (or GC / coverage filtered) top-k: candidates may sit beyond the TD window
         thr = res['dist'][:, k - 1]
@@ -276,17 +314,30 @@ def pairs_pruned(sig_padded, dt, row0=0, row1=None, k=0, topk_filter=0, want_cou
             thr = torch.cat([thr, thr.new_full((rows_pad,), float('-inf'))])
         t_r = thr.view(n_rt, T).amax(1)
         more = (lb <= t_r[:, None]) & ~need
-        if bool(more.any().item()):
-            sp2, v2 = lists(more)
+        n_aff = int(more.any(1).sum().item())
+        if n_aff:
+            # only the affected row tiles run again (they sort first: the others have empty lists); their rows' lists
+            # are merged with the first sweep's in the (distance, id) order
+            sp2, v2 = lists(more, active=n_aff)
             visited += v2
             r2 = pairs(sig_s, st, row0, row1, k=k, topk_filter=topk_filter, want_count=False, metric=metric, sparse=sp2)
-            d = torch.cat([res['dist'], r2['dist']], 1)
-            j = torch.cat([res['idx'], r2['idx']], 1)
+            aff = sp2[1][:n_aff].to(torch.int64)
+            rows_aff = (aff[:, None] * T + torch.arange(T, device=dev)[None, :]).flatten()
+            rows_aff = rows_aff[rows_aff < (row1 - row0)]
+            d = torch.cat([res['dist'][rows_aff], r2['dist'][rows_aff]], 1)
+            j = torch.cat([res['idx'][rows_aff], r2['idx'][rows_aff]], 1)
             jkey = torch.where(j < 0, torch.full_like(j, 2 ** 31 - 1), j)
             o1 = torch.argsort(jkey, dim=1, stable=True)
             d, j = d.gather(1, o1), j.gather(1, o1)
             o2 = torch.argsort(d, dim=1, stable=True)[:, :k]
-            res['dist'], res['idx'] = d.gather(1, o2).contiguous(), j.gather(1, o2).contiguous()
+            res['dist'][rows_aff] = d.gather(1, o2)
+            res['idx'][rows_aff] = j.gather(1, o2)
+    mark('second sweep + merge')
+    if timings is not None:
+        torch.cuda.synchronize()
+        for (_, e0), (name, e1) in zip(marks, marks[1:]):
+            timings[name] = e0.elapsed_time(e1)
+        timings['tiles_first'], timings['tiles_second'] = visited1, visited - visited1
     res['row_ids'] = perm[row0:row1]
     res['tiles_visited'], res['tiles_total'] = visited, n_rt * n_ct
     return res

@@ -154,6 +154,10 @@ typedef struct {
   const int32_t* item_order;
   const int64_t* tile_off;
   const int32_t* tile_list;
+  int32_t split_all;           /* > 0: every row tile is swept as this many segments (items), merged afterwards; 0: the
+                                  library splits only the row tiles of the last partial wave */
+  int32_t n_active_row_tiles;  /* > 0: only the first so many row tiles of item_order are processed (the outputs of
+                                  the other rows are left untouched); 0: all */
 } dbb_pairs_input;
 
 typedef struct {

@@ -296,7 +296,7 @@ def test_pruned_sweep_equals_full_sweep():
         dt = device.DevicePairTables(tables)
         cnt = tables.td_bound is not None                              # without a bound every pair counts: nothing to skip
         full = device.pairs(sig, dt, k=20, topk_filter=filt, want_count=cnt)
-        pr = device.pairs_pruned(sig, dt, k=20, topk_filter=filt, want_count=cnt)
+        pr = device.pairs_pruned(sig, dt, k=20, topk_filter=filt, want_count=cnt, n_classes=(1 if filt == device.FILTER_TD else 3))
         got = device.unsort_rows(pr, n)
         for key in ('idx', 'dist') + (('count', 'neighbour_bp') if cnt else ()):
             assert torch.equal(got[key], full[key]), (key, filt)
