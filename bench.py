@@ -336,6 +336,16 @@ def run_ours(args):
 
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     result = {}
+    sig_keep = [None]
+    phase_events, timed_now = [], [False]
+
+    def stage2(sig_all):
+        # [r0, r1) is this rank's row block: of the caller's order for the full sweep, of the sorted order for the
+        # pruned one (every rank derives the same sort from the gathered signatures)
+        if args.no_prune:
+            return device.pairs(sig_all, dt, r0, r1, k=K_NN, topk_filter=topk_filter, want_count=True)
+        return device.pairs_pruned(sig_all, dt, r0, r1, k=K_NN, topk_filter=topk_filter, want_count=True,
+                                   timings=phase_events if timed_now[0] else None)
 
     def step(e=None):
         if e: e[0].record()
@@ -343,9 +353,10 @@ def run_ours(args):
         if e: e[1].record()
         if not counting_only:
             sig_all = parallel.all_gather_rows(freq, shard_counts)
+            sig_keep[0] = sig_all
         if e: e[2].record()
         if not counting_only:
-            result['knn'] = device.pairs(sig_all, dt, r0, r1, k=K_NN, topk_filter=topk_filter, want_count=True)
+            result['knn'] = stage2(sig_all)
         if e: e[3].record()
 
     for _ in range(max(args.warmup, 3)):
@@ -354,8 +365,10 @@ def run_ours(args):
     sampler = ClockSampler(local); sampler.start()
     t_start = torch.cuda.Event(enable_timing=True); t_end = torch.cuda.Event(enable_timing=True)
     t_start.record()
+    timed_now[0] = True
     for s in range(args.steps):
         step(ev[s])
+    timed_now[0] = False
     t_end.record()
     torch.cuda.synchronize(); barrier()
     clocks = sampler.stop()
@@ -371,7 +384,12 @@ def run_ours(args):
     ms_knn = max_over_ranks(sum(e[2].elapsed_time(e[3]) for e in ev) / args.steps)
     ms_step = total_ms / args.steps
     pairs_total = float(n_total) * float(n_total)
-    launches_per_step = plan.launches + (0 if counting_only else int(_lib.lib().dbb_pairs_launches(n_total, r1 - r0)))
+    if counting_only:
+        launches_per_step = plan.launches
+    elif args.no_prune:
+        launches_per_step = plan.launches + int(_lib.lib().dbb_pairs_launches(n_total, r1 - r0))
+    else:
+        launches_per_step = plan.launches + int(result['knn']['launches'])     # pairs + merge kernels of one or two sweeps
 
     e2e_s = e2e_count_s = None
     h2d = d2h = 0
@@ -390,14 +408,14 @@ def run_ours(args):
             _lib.check(L.dbb_tetra_signatures_host(_lib.ptr(a_np), _lib.ptr(seq_off), my_n, _lib.ptr(h_counts), _lib.ptr(h_freq)))
 
         def e2e_pairs():
-            if world == 1:
+            if world == 1 and args.no_prune:
                 return _pairs.run_pairs_host(h_freq, tables, k=K_NN, topk_filter=topk_filter, want_count=True)
-            # N > 1: the host-produced signatures are gathered through the device, then the row block runs
-            # with its results copied back to the host
+            # the host-produced signatures go up (and, N > 1, are gathered through the device), the row block runs,
+            # its results are copied back to the host
             f = torch.from_numpy(h_freq).to(dev, non_blocking=True)
             sig_all = parallel.all_gather_rows(device.pad_signatures(f), shard_counts)
-            res = device.pairs(sig_all, dt, r0, r1, k=K_NN, topk_filter=topk_filter, want_count=True)
-            return {k_: v.cpu() for k_, v in res.items()}
+            res = stage2(sig_all)
+            return {k_: v.cpu() for k_, v in res.items() if torch.is_tensor(v)}
 
         e2e_steps = max(1, min(args.steps, 5))
         e2e_count(); e2e_pairs()
@@ -432,6 +450,15 @@ def run_ours(args):
             ok &= bool(np.array_equal(hc[i], O.seq_counts_np(s)))
         if not args.no_e2e:
             ok &= bool(np.array_equal(h_counts.astype(np.int64), hc))
+        if not counting_only and not args.no_prune:
+            # the pruned sweep against the full sweep of the same row block: identical, bit for bit
+            kn = result['knn']
+            ids = kn['row_ids']
+            full = device.pairs(sig_keep[0], dt, 0, n_total, k=K_NN,
+                                topk_filter=topk_filter, want_count=True) if n_total <= 300000 else None
+            if full is not None:
+                for key in ('idx', 'dist', 'count', 'neighbour_bp'):
+                    ok &= bool(torch.equal(kn[key], full[key][ids]))
         verified = ok
         if not ok:
             raise SystemExit('bench.py: parity spot check FAILED (counts differ from the oracle)')
@@ -448,7 +475,29 @@ def run_ours(args):
     traffic = load_traffic()
     gbs = alg_bytes / (ms_count * 1e-3) / 1e9
     fp32_peak = sm_count * 128 * sm_max_mhz * 1e6
-    lane_ops = 272.0 * rows * n_total / (ms_knn * 1e-3)
+    pruning = None
+    pairs_executed = float(rows) * float(n_total)
+    if not counting_only and not args.no_prune:
+        kn = result['knn']
+        pruning = {'tiles_visited': int(kn['tiles_visited']), 'tiles_total': int(kn['tiles_total']),
+                   'frac_visited': kn['tiles_visited'] / max(kn['tiles_total'], 1),
+                   'what': 'exact: scaffolds sorted by (TD-bound class, GC projection p of the signature); L1 >= 2|p_a - p_b| lets whole '
+                           '128 x 128 tiles be skipped; results identical to the full sweep (checked below)'}
+        pairs_executed = min(pairs_executed, kn['tiles_visited'] * 128.0 * 128.0)
+    ms_kernels = ms_knn
+    if phase_events:
+        # pairs_kernel + merge_kernel launches only (the sweeps), without the planning ops around them
+        per_step = []
+        for marks in phase_events:
+            d = {name: e0.elapsed_time(e1) for (_, e0), (name, e1) in zip(marks, marks[1:])}
+            per_step.append(d)
+        ms_plan = sum(d['plan'] for d in per_step) / len(per_step)
+        ms_sweep = sum(d['sweep'] for d in per_step) / len(per_step)
+        ms_second = sum(d['second sweep + merge'] for d in per_step) / len(per_step)
+        ms_kernels = ms_sweep + (ms_second if pruning and int(result['knn']['launches']) > 2 else 0.0)
+        pruning.update({'ms_plan': ms_plan, 'ms_sweep': ms_sweep, 'ms_second_sweep_and_merge': ms_second})
+    lane_ops = 272.0 * pairs_executed / (ms_kernels * 1e-3)        # executed work only (rank 0's row block)
+    lane_ops_resolved = 272.0 * float(rows) * float(n_total) / (ms_knn * 1e-3)
     line = {
         'metric': METRIC,
         'value': total_bp / (ms_count * 1e-3) / 1e9, 'unit': 'Gbp/s',
@@ -463,13 +512,20 @@ def run_ours(args):
                      'algorithmic_bytes': alg_bytes, 'peak_source': peak_src},
         'roofline_pairs': None if counting_only else {'kernel': 'pairs_kernel (stage 2)', 'bound': 'fp32', 'achieved': lane_ops / 1e12,
                            'peak': fp32_peak / 1e12, 'unit': 'T lane-op/s', 'frac': lane_ops / fp32_peak,
-                           'traffic': traffic.get('pairs_dram_bytes_per_step') if args.workload == 'C2' and args.scale == 1.0 and world == 1 else None,
+                           'pairs_resolved_per_executed': float(rows) * float(n_total) / max(pairs_executed, 1.0),
+                           'frac_resolved': lane_ops_resolved / fp32_peak,
+                           'note': 'achieved / frac: lane-ops of the pairs actually computed over the time of the sweep launches; frac_resolved: '
+                                   '272 lane-ops for every pair of the N x N problem over the whole stage (planning included), i.e. what a full sweep '
+                                   'would have to sustain to be as fast',
+                           'traffic': traffic.get('pairs_dram_bytes_per_step') if args.workload == 'C2' and args.scale == 1.0 and world == 1 and args.no_prune else None,
                            'peak_source': '%d SMs x 128 FP32 lanes x %.0f MHz (272 lane-ops per pair)' % (sm_count, sm_max_mhz)},
         'e2e': None if args.no_e2e else {'value': total_bp / e2e_count_s / 1e9, 'unit': 'Gbp/s', 'value2': pairs_total / max(e2e_s - e2e_count_s, 1e-9),
                 'unit2': 'scaffold-pairs/s', 'ms_per_step': e2e_s * 1e3, 'steps': e2e_steps,
                 'pipeline_gbp_per_s': total_bp / e2e_s / 1e9, 'pipeline_pairs_per_s': pairs_total / e2e_s,
                 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                'api': 'dbb_tetra_signatures_host + dbb_pairs_host (pinned host buffers)'},
+                'api': 'dbb_tetra_signatures_host + dbb_pairs_host (pinned host buffers)' if args.no_prune else
+                       'dbb_tetra_signatures_host (pinned host buffers) + H2D of the signatures, device.pairs_pruned, D2H of the results'},
+        'pruning': pruning,
         'gpu_launches': launches_per_step * args.steps, 'launches_per_step': launches_per_step,
         'clocks': clocks, 'verified_vs_oracle': verified,
         'shard': {'scaffolds_rank0': my_n, 'bp_rank0': my_bp, 'lpt_imbalance': parallel.imbalance(meta.length, parts),
@@ -502,6 +558,7 @@ def main():
     ap.add_argument('--scale', type=float, default=1.0, help='fraction of the C2 scaffold count (tests only; 1.0 = the named config)')
     ap.add_argument('--cpu-seconds', type=float, default=8.0, help='target wall time of each CPU-baseline leg')
     ap.add_argument('--no-cpu', action='store_true', help='skip the CPU baseline leg')
+    ap.add_argument('--no-prune', action='store_true', help='stage 2 as a full sweep over all column tiles (default: exact tile skipping, device.pairs_pruned)')
     ap.add_argument('--no-e2e', action='store_true', help='skip the host-buffer end-to-end leg (large exploratory workloads)')
     ap.add_argument('--workload', default='C2', choices=['C2', 'C3', 'C4', 'C5'], help='C2 = the benchmark of record (weak scaling); C3 = 250k scaffolds with GC + coverage filters, C4 = 1M scaffolds, C5 = 10M short contigs + 8 x 5 Mb, counting only (all strong scaling)')
     args = ap.parse_args()

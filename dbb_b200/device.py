@@ -333,13 +333,16 @@ def pairs_pruned(sig_padded, dt, row0=0, row1=None, k=0, topk_filter=0, want_cou
             res['dist'][rows_aff] = d.gather(1, o2)
             res['idx'][rows_aff] = j.gather(1, o2)
     mark('second sweep + merge')
-    if timings is not None:
+    if isinstance(timings, list):
+        timings.append(marks)                      # events only; the caller reads them after its own synchronisation
+    elif timings is not None:
         torch.cuda.synchronize()
         for (_, e0), (name, e1) in zip(marks, marks[1:]):
             timings[name] = e0.elapsed_time(e1)
         timings['tiles_first'], timings['tiles_second'] = visited1, visited - visited1
     res['row_ids'] = perm[row0:row1]
     res['tiles_visited'], res['tiles_total'] = visited, n_rt * n_ct
+    res['launches'] = 2 if visited == visited1 else 4            # pairs_kernel + merge_kernel per sweep
     return res
 
 
