@@ -344,8 +344,8 @@ def run_ours(args):
         # pruned one (every rank derives the same sort from the gathered signatures)
         if args.no_prune:
             return device.pairs(sig_all, dt, r0, r1, k=K_NN, topk_filter=topk_filter, want_count=True)
-        return device.pairs_pruned(sig_all, dt, r0, r1, k=K_NN, topk_filter=topk_filter, want_count=True,
-                                   timings=phase_events if timed_now[0] else None)
+        return device.pairs_pruned(sig_all, dt, k=K_NN, topk_filter=topk_filter, want_count=True,
+                                   timings=phase_events if timed_now[0] else None, part=(rank, world) if world > 1 else None)
 
     def step(e=None):
         if e: e[0].record()
@@ -483,7 +483,8 @@ def run_ours(args):
                    'frac_visited': kn['tiles_visited'] / max(kn['tiles_total'], 1),
                    'what': 'exact: scaffolds sorted by (TD-bound class, GC projection p of the signature); L1 >= 2|p_a - p_b| lets whole '
                            '128 x 128 tiles be skipped; results identical to the full sweep (checked below)'}
-        pairs_executed = min(pairs_executed, kn['tiles_visited'] * 128.0 * 128.0)
+        rows = int(kn['row_ids'].shape[0])
+        pairs_executed = min(float(rows) * float(n_total), kn['tiles_visited'] * 128.0 * 128.0)
     ms_kernels = ms_knn
     if phase_events:
         # pairs_kernel + merge_kernel launches only (the sweeps), without the planning ops around them

@@ -206,7 +206,7 @@ class _SortedTables(object):
 
 
 def pairs_pruned(sig_padded, dt, row0=0, row1=None, k=0, topk_filter=0, want_count=True, metric='l1', margin=1e-5,
-                 n_classes=8, timings=None):
+                 n_classes=8, timings=None, part=None):
     """Same results as ``pairs`` (no masks), skipping 128 x 128 tiles of the pair matrix that cannot matter.
 
     Signatures sum to 1, so for ANY weights w_k in [0, 1] and p = sum_k w_k sig_k:  L1(a, b) >= 2 |p_a - p_b|
@@ -219,7 +219,9 @@ def pairs_pruned(sig_padded, dt, row0=0, row1=None, k=0, topk_filter=0, want_cou
     The sort key is (TD-bound class, p): the bound of a pair is the bound of its shorter scaffold, so tiles of long
     scaffolds (small bounds) only need their near neighbours among each other; ``n_classes`` equal-count classes of the
     per-scaffold bound keep the tiles homogeneous (any arrangement is exact, the intervals are taken per tile).
-    [row0, row1) are positions in the sorted order (multi-GPU: equal blocks of it); the dict carries ``row_ids``,
+    part=(rank, world): multi-GPU -- the row tiles of the sorted order are dealt to the ranks by decreasing work (their
+    tile lists differ in length by an order of magnitude, contiguous blocks would not balance); the rank's results are
+    returned for its rows only.  Otherwise [row0, row1) are positions in the sorted order.  The dict carries ``row_ids``,
     the original ids of the returned rows, and ``tiles_visited`` / ``tiles_total``.  Planning (projection, sort,
     gathers, tile mask) uses torch ops on the device; the distance work is the same pairs_kernel."""
     require_cuda()
@@ -228,6 +230,8 @@ def pairs_pruned(sig_padded, dt, row0=0, row1=None, k=0, topk_filter=0, want_cou
     if want_count and dt.td_bound is None:
         raise ValueError('pairs_pruned: without a TD bound every pair may count, nothing can be skipped (use pairs)')
     n = dt.n
+    if part is not None:
+        row0, row1 = 0, n
     row1 = n if row1 is None else row1
     dev = sig_padded.device
     T = 128
@@ -283,6 +287,13 @@ def pairs_pruned(sig_padded, dt, row0=0, row1=None, k=0, topk_filter=0, want_cou
     else:
         need = lb <= 0
     col_id = perm.to(torch.int32)
+    mine = None
+    if part is not None:
+        rank, world = part
+        by_work = torch.argsort(need.sum(1), descending=True, stable=True)
+        mine = torch.zeros(n_rt, dtype=torch.bool, device=dev)
+        mine[by_work[rank::world]] = True
+        need = need & mine[:, None]
 
     def lists(mask, active=None):
         # every row tile visits its tiles nearest (smallest lower bound) first: the top-k threshold tightens at once
@@ -301,7 +312,7 @@ def pairs_pruned(sig_padded, dt, row0=0, row1=None, k=0, topk_filter=0, want_cou
         split = int(min(8, max(1, -(-1480 // max(n_act, 1)))))
         return (col_id, order, off, tl, split, 0 if active is None else active), int(off[-1].item())
 
-    sp, visited = lists(need)
+    sp, visited = lists(need, active=None if mine is None else int(mine.sum().item()))
     mark('plan')
     res = pairs(sig_s, st, row0, row1, k=k, topk_filter=topk_filter, want_count=want_count, metric=metric, sparse=sp)
     mark('sweep')
@@ -314,6 +325,8 @@ def pairs_pruned(sig_padded, dt, row0=0, row1=None, k=0, topk_filter=0, want_cou
             thr = torch.cat([thr, thr.new_full((rows_pad,), float('-inf'))])
         t_r = thr.view(n_rt, T).amax(1)
         more = (lb <= t_r[:, None]) & ~need
+        if mine is not None:
+            more = more & mine[:, None]
         n_aff = int(more.any(1).sum().item())
         if n_aff:
             # only the affected row tiles run again (they sort first: the others have empty lists); their rows' lists
@@ -340,8 +353,16 @@ def pairs_pruned(sig_padded, dt, row0=0, row1=None, k=0, topk_filter=0, want_cou
         for (_, e0), (name, e1) in zip(marks, marks[1:]):
             timings[name] = e0.elapsed_time(e1)
         timings['tiles_first'], timings['tiles_second'] = visited1, visited - visited1
-    res['row_ids'] = perm[row0:row1]
-    res['tiles_visited'], res['tiles_total'] = visited, n_rt * n_ct
+    if mine is None:
+        res['row_ids'] = perm[row0:row1]
+    else:
+        rows_mine = (mine.nonzero()[:, 0][:, None] * T + torch.arange(T, device=dev)[None, :]).flatten()
+        rows_mine = rows_mine[rows_mine < n]
+        for key_ in ('idx', 'dist', 'count', 'neighbour_bp'):
+            if key_ in res:
+                res[key_] = res[key_][rows_mine]
+        res['row_ids'] = perm[rows_mine]
+    res['tiles_visited'], res['tiles_total'] = visited, (n_rt if mine is None else int(mine.sum().item())) * n_ct
     res['launches'] = 2 if visited == visited1 else 4            # pairs_kernel + merge_kernel per sweep
     return res
 

@@ -304,7 +304,19 @@ def test_pruned_sweep_equals_full_sweep():
     assert skipped[1] > 0.05                                           # the TD-filtered case really skips tiles
     with pytest.raises(ValueError):
         device.pairs_pruned(sig, device.DevicePairTables(cases[3][0]), k=20, want_count=True)
-    # row blocks of the sorted order (what each GPU takes): together they are the full result
+    # row tiles dealt to three ranks by work (what each GPU takes): together they are the full result
+    dt3 = device.DevicePairTables(cases[0][0])
+    full3 = device.pairs(sig, dt3, k=20, want_count=True)
+    seen = torch.zeros(n, dtype=torch.bool, device='cuda')
+    for rank in range(3):
+        part = device.pairs_pruned(sig, dt3, k=20, want_count=True, part=(rank, 3))
+        ids = part['row_ids']
+        assert not bool(seen[ids].any())
+        seen[ids] = True
+        for key in ('idx', 'dist', 'count', 'neighbour_bp'):
+            assert torch.equal(part[key], full3[key][ids]), (key, rank)
+    assert bool(seen.all())
+    # row blocks of the sorted order: together they are the full result
     dt = device.DevicePairTables(cases[0][0])
     full = device.pairs(sig, dt, k=20, want_count=True)
     for r0, r1 in ((0, 900), (900, 1700), (1700, n)):
