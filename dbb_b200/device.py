@@ -190,13 +190,15 @@ _GC_WEIGHTS = None
 
 
 def projection_weights(device):
-    """float32[140]: GC fraction of every canonical tetramer (0, .25, .5, .75, 1), zero for the padding columns.
-    Any weights in [0, 1] give the bound used by pairs_pruned; these spread metagenomes by their GC content."""
+    """float32[140]: per canonical tetramer 0 / 0.5 / 1 for <= 1 / 2 / >= 3 G or C, zero for the padding columns.
+    Any weights in [0, 1] give the bound used by pairs_pruned; these spread metagenomes by their GC content, and the
+    saturated form keeps more of the distance than the plain GC fraction (0, .25, .5, .75, 1): on the synthetic C2 / C4
+    inputs the pair-level bound leaves 29 % / 33 % of the pairs instead of 40 % / 44 %."""
     global _GC_WEIGHTS
     if _GC_WEIGHTS is None:
         names, _ = _lib.kmer_table()
         w = np.zeros(_lib.SIG_STRIDE, dtype=np.float32)
-        w[:_lib.NUM_KMERS] = [sum(ch in 'GC' for ch in nm) / 4.0 for nm in names]
+        w[:_lib.NUM_KMERS] = [min(1.0, max(0.0, (sum(ch in 'GC' for ch in nm) - 1) / 2.0)) for nm in names]
         _GC_WEIGHTS = w
     return torch.from_numpy(_GC_WEIGHTS).to(device)
 
