@@ -187,6 +187,7 @@ def pairs(sig_padded, dt, row0=0, row1=None, k=0, topk_filter=0, want_count=True
 
 
 _GC_WEIGHTS = None
+_ITEMS_TARGET = int(__import__('os').environ.get('DBB_PRUNE_ITEMS', '740'))    # work items per sweep (~5 per SM; C2: 2 segments per row tile 12.3 ms, 1: 17.8, 4: 13.4)
 
 
 def projection_weights(device):
@@ -297,7 +298,7 @@ def pairs_pruned(sig_padded, dt, row0=0, row1=None, k=0, topk_filter=0, want_cou
         mine[by_work[rank::world]] = True
         need = need & mine[:, None]
 
-    def lists(mask, active=None):
+    def lists(mask, active=None, target=_ITEMS_TARGET):
         # every row tile visits its tiles nearest (smallest lower bound) first: the top-k threshold tightens at once
         # and the far tiles add next to nothing (in ascending tile order every tile would bring better candidates
         # than the one before -- the worst case for a streaming top-k)
@@ -309,9 +310,10 @@ def pairs_pruned(sig_padded, dt, row0=0, row1=None, k=0, topk_filter=0, want_cou
         keep = torch.arange(n_ct, device=dev)[None, :] < cnt[:, None]
         tl = by_lb[keep].to(torch.int32).contiguous()
         order = torch.argsort(cnt, descending=True, stable=True).to(torch.int32)   # most work first; empty lists last
-        # ~10 work items per SM: the lists differ in length by an order of magnitude, whole row tiles do not balance
+        # ~5 work items per SM: the lists differ in length by an order of magnitude, whole row tiles do not balance,
+        # but every extra segment refills its own top-k lists
         n_act = n_rt if active is None else active
-        split = int(min(8, max(1, -(-1480 // max(n_act, 1)))))
+        split = int(min(8, max(1, -(-target // max(n_act, 1)))))
         return (col_id, order, off, tl, split, 0 if active is None else active), int(off[-1].item())
 
     sp, visited = lists(need, active=None if mine is None else int(mine.sum().item()))
@@ -333,7 +335,7 @@ def pairs_pruned(sig_padded, dt, row0=0, row1=None, k=0, topk_filter=0, want_cou
         if n_aff:
             # only the affected row tiles run again (they sort first: the others have empty lists); their rows' lists
             # are merged with the first sweep's in the (distance, id) order
-            sp2, v2 = lists(more, active=n_aff)
+            sp2, v2 = lists(more, active=n_aff, target=2 * _ITEMS_TARGET)     # few row tiles, short lists: cut finer
             visited += v2
             r2 = pairs(sig_s, st, row0, row1, k=k, topk_filter=topk_filter, want_count=False, metric=metric, sparse=sp2)
             aff = sp2[1][:n_aff].to(torch.int64)
