@@ -324,3 +324,29 @@ def test_pruned_sweep_equals_full_sweep():
         ids = part['row_ids']
         for key in ('idx', 'dist', 'count', 'neighbour_bp'):
             assert torch.equal(part[key], full[key][ids]), (key, r0)
+
+
+def test_tdneighbours_knn_public_api_pruned_and_plain_agree_with_the_oracle():
+    """TdNeighbours.knn (the array-native addition of SURVEY 8b): the default (pruned sweep) and prune=False (plain sweep
+    through dbb_pairs_host) return the same arrays, and those match the oracle's k-NN and TD neighbourhood sizes."""
+    from dbb_b200.tdNeighbours import TdNeighbours
+    meta, sig64 = _metagenome(25, 1500, gmax=40000)
+    td, gcd, cvd = _dists()
+    n = meta.n_scaffolds
+    rows = list(range(n))
+    a = TdNeighbours(None).knn(sig64, meta.length, k=20, tdDist=td, tdDistPer=80)
+    b = TdNeighbours(None).knn(sig64, meta.length, k=20, tdDist=td, tdDistPer=80, prune=False)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    s32 = sig64.astype(np.float32).astype(np.float64)
+    d64 = O.l1_rows_np(s32, rows)
+    util.check_topk(a[0], a[1].astype(np.float64), d64, rows, 20)
+    ot = O.DistTables(tdDist=td, tdDistPer=80)
+    o_td = O.td_rows_np(s32, meta.length, rows, ot, None)
+    assert np.abs(a[2] - o_td.sum(axis=1)).max() <= 1
+    c = TdNeighbours(None).knn(sig64, meta.length, GC=meta.gc_obs, cov=meta.coverage, k=10, tdDist=td, tdDistPer=80, gcDist=gcd,
+                               gcDistPer=80, covDist=cvd, covDistPer=80)
+    d = TdNeighbours(None).knn(sig64, meta.length, GC=meta.gc_obs, cov=meta.coverage, k=10, tdDist=td, tdDistPer=80, gcDist=gcd,
+                               gcDistPer=80, covDist=cvd, covDistPer=80, prune=False)
+    for x, y in zip(c, d):
+        assert np.array_equal(x, y)
