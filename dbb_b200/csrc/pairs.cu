@@ -189,11 +189,18 @@ __device__ __forceinline__ void add_bp(SmemLayout& sm, int lr, uint32_t v) {
 
 __device__ __forceinline__ bool cov_predicate(double cu, double cc, double lo, double hi);
 
+// the caller's id of column position j (the lists hold positions; ids only decide exact distance ties and are
+// substituted when the lists are written out)
+__device__ __forceinline__ int32_t id_of(const int32_t* col_id, int32_t j) {
+  return (col_id && j != INT_MAX) ? __ldg(col_id + j) : j;
+}
+
 // warp-cooperative insertion of (d, c) into the sorted list of `row`; returns the new k-th best
-__device__ __forceinline__ float list_insert(SmemLayout& sm, int row, float d, int32_t c, int k, int lane) {
+__device__ __forceinline__ float list_insert(SmemLayout& sm, int row, float d, int32_t c, int k, int lane, const int32_t* col_id) {
   float ed = sm.list_d[row][lane];
   int32_t ej = sm.list_j[row][lane];
-  const bool before = (ed < d) || (ed == d && ej < c);
+  bool before = ed < d;
+  if (ed == d) before = id_of(col_id, ej) < id_of(col_id, c);      // rare: an exact tie
   const int pos = __popc(__ballot_sync(0xffffffffu, before));
   float pd = __shfl_up_sync(0xffffffffu, ed, 1);
   int32_t pj = __shfl_up_sync(0xffffffffu, ej, 1);
@@ -283,9 +290,8 @@ __device__ __noinline__ void process_row_pair(const Params& P, int par, int warp
         const int crow = lr0 + (src >> 4);
         const float cd = __shfl_sync(0xffffffffu, d, src);
         if (cd <= sm.thr[crow]) {            // the list may have tightened since the ballot
-          int32_t cc = (int32_t)(col_base + (src & 15) + 16 * j);
-          if (P.col_id) cc = __ldg(P.col_id + cc);
-          const float nt = list_insert(sm, crow, cd, cc, k, lane);
+          const int32_t cc = (int32_t)(col_base + (src & 15) + 16 * j);
+          const float nt = list_insert(sm, crow, cd, cc, k, lane, P.col_id);
           if (lane == 0) sm.thr[crow] = nt;
         }
         __syncwarp();
@@ -436,10 +442,9 @@ __device__ __noinline__ void drain_queue(const Params& P, int par, int warp, int
         m &= m - 1;
         const int crow = __shfl_sync(0xffffffffu, lr, src);
         const float cd = __shfl_sync(0xffffffffu, d, src);
-        int32_t cc = (int32_t)__shfl_sync(0xffffffffu, (int)cj, src);
-        if (P.col_id) cc = __ldg(P.col_id + cc);
+        const int32_t cc = (int32_t)__shfl_sync(0xffffffffu, (int)cj, src);
         if (cd <= sm.thr[crow]) {          // the list may have tightened since the candidate was flagged
-          const float nt = list_insert(sm, crow, cd, cc, k, lane);
+          const float nt = list_insert(sm, crow, cd, cc, k, lane, P.col_id);
           if (lane == 0) sm.thr[crow] = nt;
         }
         __syncwarp();
@@ -820,7 +825,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pairs_kernel(const __grid_const
           const int32_t ej = sm.list_j[lr][lane];
           const float ed = sm.list_d[lr][lane];
           if (seg < 0) {
-            if (P.knn_idx) P.knn_idx[(gi - P.row0) * k + lane] = (ej == INT_MAX) ? -1 : ej;
+            if (P.knn_idx) P.knn_idx[(gi - P.row0) * k + lane] = (ej == INT_MAX) ? -1 : id_of(P.col_id, ej);
             if (P.knn_dist) P.knn_dist[(gi - P.row0) * k + lane] = ed;
           } else {
             const int64_t o = (((int64_t)srt * TILE + lr) * P.n_seg + seg) * k + lane;
@@ -861,7 +866,8 @@ __global__ void __launch_bounds__(128) merge_kernel(const Params P, int64_t n_sp
         const float d = P.part_dist[o];
         const int32_t c = P.part_idx[o];
         if (c == INT_MAX) break;              // lists are sorted: the rest is padding
-        const bool before = (ed < d) || (ed == d && ej < c);
+        bool before = ed < d;
+        if (ed == d) before = id_of(P.col_id, ej) < id_of(P.col_id, c);
         const int pos = __popc(__ballot_sync(0xffffffffu, before));
         const float pd = __shfl_up_sync(0xffffffffu, ed, 1);
         const int32_t pj = __shfl_up_sync(0xffffffffu, ej, 1);
@@ -872,7 +878,7 @@ __global__ void __launch_bounds__(128) merge_kernel(const Params P, int64_t n_sp
       }
     }
     if (lane < k) {
-      if (P.knn_idx) P.knn_idx[gi * k + lane] = (ej == INT_MAX) ? -1 : ej;
+      if (P.knn_idx) P.knn_idx[gi * k + lane] = (ej == INT_MAX) ? -1 : id_of(P.col_id, ej);
       if (P.knn_dist) P.knn_dist[gi * k + lane] = ed;
     }
   }
