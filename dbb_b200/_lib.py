@@ -53,6 +53,10 @@ class GreedyInput(ctypes.Structure):
                 ('gc_nm', c_i32), ('gc_nl', c_i32), ('cov_lo', c_vp), ('cov_hi', c_vp), ('cov_nl', c_i32)]
 
 
+class MergeInput(ctypes.Structure):
+    _fields_ = [('search', RefineInput), ('own', c_vp)]
+
+
 class RefineOutput(ctypes.Structure):
     _fields_ = [('closest', c_vp), ('min_dist', c_vp), ('assigned', c_vp), ('within', c_vp)]
 
@@ -81,6 +85,8 @@ SIGNATURES = {
     'dbb_pairs_host': (ctypes.c_int, [ctypes.POINTER(PairsInput), c_i64, c_i64, ctypes.POINTER(PairsOutput)]),
     'dbb_refine_dev': (ctypes.c_int, [ctypes.POINTER(RefineInput), ctypes.POINTER(RefineOutput), c_vp]),
     'dbb_refine_host': (ctypes.c_int, [ctypes.POINTER(RefineInput), ctypes.POINTER(RefineOutput)]),
+    'dbb_merge_table_dev': (ctypes.c_int, [ctypes.POINTER(MergeInput), c_vp, c_vp, c_vp]),
+    'dbb_merge_table_host': (ctypes.c_int, [ctypes.POINTER(MergeInput), c_vp, c_vp]),
     'dbb_greedy_host': (ctypes.c_int, [ctypes.POINTER(GreedyInput), c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'dbb_pca_gram_host': (ctypes.c_int, [c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp]),
     'dbb_pca_project_host': (ctypes.c_int, [c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_i32, c_vp]),

@@ -12,12 +12,17 @@
 // FP64 throughput is ample (one warp per unbinned contig, cores streamed from L2).
 #include "common.cuh"
 #include <algorithm>
+#include <cstring>
 
 namespace {
 
 struct RefineParams {
   dbb_refine_input in;
   dbb_refine_output out;
+  // N5 (merge.py:96-156): the queries are binned contigs; own[u] is skipped by the closest-bin search and the
+  // per-pair flags / closest bins are tallied per (own bin, other bin)
+  const int32_t* own;
+  int32_t* table;                // [B][B][6] or nullptr
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -42,6 +47,8 @@ __global__ void __launch_bounds__(256) refine_kernel(const RefineParams P) {
   const double ugc = I.u_gc[u], ucov = I.u_cov[u], tdb = I.u_td_bound[u];
   const int gcl = I.u_gc_lbin[u], covl = I.u_cov_lbin[u];
   const double cov_lo = I.cov_lo[covl], cov_hi = I.cov_hi[covl];
+  const int64_t own = P.own ? P.own[u] : -1;
+  const bool all_td = P.out.within || P.table;           // the TD flag of every core is wanted
   int best[3] = {-1, -1, -1};
   double bestd[3] = {1e9, 1e9, 1e9};                     // refineBins.py:56
 
@@ -62,7 +69,8 @@ __global__ void __launch_bounds__(256) refine_kernel(const RefineParams P) {
     }
     const uint32_t m_gc = __ballot_sync(0xffffffffu, p_gc), m_cov = __ballot_sync(0xffffffffu, p_cov);
     // the TD distance is needed for cores that passed both (or for all of them when the flag matrix is wanted)
-    uint32_t todo = P.out.within ? __ballot_sync(0xffffffffu, c < B) : (m_gc & m_cov);
+    uint32_t todo = all_td ? __ballot_sync(0xffffffffu, c < B) : (m_gc & m_cov);
+    if (own >= c0 && own < c0 + 32 && !all_td) todo &= ~(1u << (own - c0));
     uint32_t m_td = 0;
     while (todo) {
       const int j = __ffs(todo) - 1;
@@ -77,7 +85,7 @@ __global__ void __launch_bounds__(256) refine_kernel(const RefineParams P) {
       const double d = warp_sum(part);
       const bool p_td = d < tdb;                         // distributions.py:103-104 (strict)
       if (p_td) m_td |= 1u << j;
-      if (p_td && ((m_gc & m_cov) >> j & 1u)) {
+      if (p_td && ((m_gc & m_cov) >> j & 1u) && c0 + j != own) {
         const double dg = fabs(ugc - __shfl_sync(0xffffffffu, cgc, j));
         const double dc = fabs(ucov - __shfl_sync(0xffffffffu, ccov, j));
         const int ci = (int)(c0 + j);
@@ -90,11 +98,22 @@ __global__ void __launch_bounds__(256) refine_kernel(const RefineParams P) {
     }
     if (P.out.within && c < B)
       P.out.within[u * B + c] = (uint8_t)((p_gc ? 1 : 0) | (p_cov ? 2 : 0) | ((m_td >> lane & 1u) ? 4 : 0));
+    if (P.table && c < B && c != own) {                  // merge.py:112-119, bin2 != bin1
+      int32_t* t = P.table + (own * B + c) * 6;
+      if (p_gc) atomicAdd(t, 1);
+      if (p_cov) atomicAdd(t + 1, 1);
+      if (m_td >> lane & 1u) atomicAdd(t + 2, 1);
+    }
   }
   if (lane == 0) {
     if (P.out.closest) { P.out.closest[u * 3] = best[0]; P.out.closest[u * 3 + 1] = best[1]; P.out.closest[u * 3 + 2] = best[2]; }
     if (P.out.min_dist) { P.out.min_dist[u * 3] = bestd[0]; P.out.min_dist[u * 3 + 1] = bestd[1]; P.out.min_dist[u * 3 + 2] = bestd[2]; }
     if (P.out.assigned) P.out.assigned[u] = (best[0] >= 0 && best[0] == best[1] && best[0] == best[2]) ? best[0] : -1;
+    if (P.table) {                                       // merge.py:147-152
+      #pragma unroll
+      for (int i = 0; i < 3; ++i)
+        if (best[i] >= 0) atomicAdd(P.table + (own * B + best[i]) * 6 + 3 + i, 1);
+    }
   }
 }
 
@@ -123,27 +142,24 @@ int check_input(const dbb_refine_input* in, const dbb_refine_output* out) {
   return DBB_OK;
 }
 
-}  // namespace
-
-DBB_EXPORT int dbb_refine_dev(const dbb_refine_input* in, const dbb_refine_output* out, void* stream) {
-  int rc = check_input(in, out);
-  if (rc != DBB_OK || in->n_unbinned == 0) return rc;
+int launch(const dbb_refine_input* in, const dbb_refine_output* out, const int32_t* d_own, int32_t* d_table, cudaStream_t st) {
   RefineParams P;
-  P.in = *in; P.out = *out;
+  P.in = *in; P.out = *out; P.own = d_own; P.table = d_table;
   const int64_t grid = (in->n_unbinned + 7) / 8;
-  DBB_REQUIRE(grid < (1ll << 31), "too many unbinned contigs for one launch");
-  refine_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(P);
+  DBB_REQUIRE(grid < (1ll << 31), "too many query contigs for one launch");
+  if (d_table) DBB_CUDA_TRY(cudaMemsetAsync(d_table, 0, (size_t)in->n_cores * in->n_cores * 6 * sizeof(int32_t), st));
+  refine_kernel<<<(unsigned)grid, 256, 0, st>>>(P);
   DBB_CUDA_TRY(cudaGetLastError());
   return DBB_OK;
 }
 
-DBB_EXPORT int dbb_refine_host(const dbb_refine_input* in, const dbb_refine_output* out) {
-  int rc = check_input(in, out);
-  if (rc != DBB_OK || in->n_unbinned == 0) return rc;
+// host buffers in / out: uploads, one launch, downloads (own / table: the N5 variant, both or neither)
+int run_host(const dbb_refine_input* in, const dbb_refine_output* out, const int32_t* own, int32_t* table) {
   const size_t U = (size_t)in->n_unbinned, B = (size_t)in->n_cores;
+  int rc = DBB_OK;
   cudaStream_t st;
   DBB_CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-  Buf usig, csig, ugc, ucov, cgc, ccov, utd, ugl, ucl, cgm, glo, ghi, clo, chi, o_cl, o_md, o_as, o_wi;
+  Buf usig, csig, ugc, ucov, cgc, ccov, utd, ugl, ucl, cgm, glo, ghi, clo, chi, o_cl, o_md, o_as, o_wi, b_own, o_tb;
   dbb_refine_input d = *in;
   dbb_refine_output o = *out;
   do {
@@ -153,20 +169,74 @@ DBB_EXPORT int dbb_refine_host(const dbb_refine_input* in, const dbb_refine_outp
     UP(glo, gc_lo, (size_t)in->gc_nm * in->gc_nl) UP(ghi, gc_hi, (size_t)in->gc_nm * in->gc_nl)
     UP(clo, cov_lo, (size_t)in->cov_nl) UP(chi, cov_hi, (size_t)in->cov_nl)
 #undef UP
+    if (own && (rc = b_own.up(own, U, st)) != DBB_OK) break;
+    if (table && (rc = o_tb.alloc(B * B * 6 * sizeof(int32_t))) != DBB_OK) break;
     if (out->closest) { if ((rc = o_cl.alloc(U * 12)) != DBB_OK) break; o.closest = (int32_t*)o_cl.p; }
     if (out->min_dist) { if ((rc = o_md.alloc(U * 24)) != DBB_OK) break; o.min_dist = (double*)o_md.p; }
     if (out->assigned) { if ((rc = o_as.alloc(U * 4)) != DBB_OK) break; o.assigned = (int32_t*)o_as.p; }
     if (out->within) { if ((rc = o_wi.alloc(U * std::max<size_t>(B, 1))) != DBB_OK) break; o.within = (uint8_t*)o_wi.p; }
-    if ((rc = dbb_refine_dev(&d, &o, st)) != DBB_OK) break;
+    if ((rc = launch(&d, &o, (const int32_t*)b_own.p, (int32_t*)o_tb.p, st)) != DBB_OK) break;
     cudaError_t e = cudaSuccess;
     if (out->closest) e = cudaMemcpyAsync(out->closest, o.closest, U * 12, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess && out->min_dist) e = cudaMemcpyAsync(out->min_dist, o.min_dist, U * 24, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess && out->assigned) e = cudaMemcpyAsync(out->assigned, o.assigned, U * 4, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess && out->within && B) e = cudaMemcpyAsync(out->within, o.within, U * B, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && table && B) e = cudaMemcpyAsync(table, o_tb.p, B * B * 6 * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    if (e != cudaSuccess) { dbb::set_error("dbb_refine_host failed: %s", cudaGetErrorString(e)); rc = DBB_ERR_CUDA; }
+    if (e != cudaSuccess) { dbb::set_error("filtered nearest-core search failed: %s", cudaGetErrorString(e)); rc = DBB_ERR_CUDA; }
   } while (0);
   cudaStreamSynchronize(st);
   cudaStreamDestroy(st);
   return rc;
+}
+
+int check_merge(const dbb_merge_input* in, const int32_t* table) {
+  DBB_REQUIRE(in && table, "NULL argument");
+  DBB_REQUIRE(in->search.n_unbinned == 0 || in->own, "own bin of every contig is required");
+  DBB_REQUIRE(in->search.n_cores < 18919, "too many bins for an int32 [B][B][6] table");
+  return DBB_OK;
+}
+
+}  // namespace
+
+DBB_EXPORT int dbb_refine_dev(const dbb_refine_input* in, const dbb_refine_output* out, void* stream) {
+  int rc = check_input(in, out);
+  if (rc != DBB_OK || in->n_unbinned == 0) return rc;
+  return launch(in, out, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+DBB_EXPORT int dbb_refine_host(const dbb_refine_input* in, const dbb_refine_output* out) {
+  int rc = check_input(in, out);
+  if (rc != DBB_OK || in->n_unbinned == 0) return rc;
+  return run_host(in, out, nullptr, nullptr);
+}
+
+// N5: merge.py:96-156.  own[] values are the caller's responsibility on the device entry point; the host entry
+// point checks them.
+DBB_EXPORT int dbb_merge_table_dev(const dbb_merge_input* in, int32_t* d_table, int32_t* d_closest, void* stream) {
+  int rc = check_merge(in, d_table);
+  if (rc != DBB_OK) return rc;
+  dbb_refine_output out = {d_closest, nullptr, nullptr, nullptr};
+  dbb_refine_output chk = out;
+  chk.assigned = reinterpret_cast<int32_t*>(d_table);     // "some output requested" for check_input
+  if ((rc = check_input(&in->search, &chk)) != DBB_OK) return rc;
+  if (in->search.n_unbinned == 0) {
+    DBB_CUDA_TRY(cudaMemsetAsync(d_table, 0, (size_t)in->search.n_cores * in->search.n_cores * 6 * sizeof(int32_t), (cudaStream_t)stream));
+    return DBB_OK;
+  }
+  return launch(&in->search, &out, in->own, d_table, (cudaStream_t)stream);
+}
+
+DBB_EXPORT int dbb_merge_table_host(const dbb_merge_input* in, int32_t* table, int32_t* closest) {
+  int rc = check_merge(in, table);
+  if (rc != DBB_OK) return rc;
+  dbb_refine_output out = {closest, nullptr, nullptr, nullptr};
+  dbb_refine_output chk = out;
+  chk.assigned = table;
+  if ((rc = check_input(&in->search, &chk)) != DBB_OK) return rc;
+  const int64_t U = in->search.n_unbinned, B = in->search.n_cores;
+  memset(table, 0, (size_t)B * B * 6 * sizeof(int32_t));
+  if (U == 0) return DBB_OK;
+  for (int64_t u = 0; u < U; ++u) DBB_REQUIRE(in->own[u] >= 0 && in->own[u] < B, "own[] out of range");
+  return run_host(&in->search, &out, in->own, table);
 }

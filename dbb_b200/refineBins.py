@@ -40,6 +40,37 @@ def coreStatistics(binnedContigs, numKmers=_lib.NUM_KMERS):
     return cores
 
 
+def searchInput(queryContigs, core_list, gcDist, gcDistPer, tdDist, tdDistPer, covDist, covDistPer):
+    """The C ABI's ``dbb_refine_input`` for ``queryContigs`` against ``core_list`` (in that order): every nearest-key
+    lookup of distributions.py depends on one contig or one core only, so it is resolved here once per object
+    instead of once per pair.  Returns (struct, arrays that must stay alive while it is in use)."""
+    U, B = len(queryContigs), len(core_list)
+    dist = Distributions(gcDist, gcDistPer, tdDist, tdDistPer, covDist, covDistPer)
+    u_len = np.array([c.length for c in queryContigs], dtype=np.float64)
+    arr = lambda it, dt=np.float64: np.ascontiguousarray(np.array(list(it), dtype=dt))
+    u_sig = np.ascontiguousarray(np.array([c.tetraSig for c in queryContigs], dtype=np.float64).reshape(U, _lib.NUM_KMERS))
+    c_sig = np.ascontiguousarray(np.array([c.tetraSig for c in core_list], dtype=np.float64).reshape(B, _lib.NUM_KMERS))
+    u_gc, u_cov = arr(c.GC for c in queryContigs), arr(c.coverage for c in queryContigs)
+    c_gc, c_cov = arr(c.GC for c in core_list), arr(c.coverage for c in core_list)
+    td_lens = _sorted_keys(tdDist)
+    u_tdb = np.ascontiguousarray(np.array([tdDist[l][dist.tdKey] for l in td_lens])[nearest_index(td_lens, u_len)])
+    means = _sorted_keys(gcDist)
+    gc_lens = _sorted_keys(gcDist[means[0]])
+    cov_lens = _sorted_keys(covDist)
+    u_gcl, u_covl = nearest_index(gc_lens, u_len), nearest_index(cov_lens, u_len)
+    c_gcm = nearest_index(means, c_gc)
+    gc_lo = np.array([[gcDist[m][l][dist.gcLowerBoundKey] for l in gc_lens] for m in means], dtype=np.float64)
+    gc_hi = np.array([[gcDist[m][l][dist.gcUpperBoundKey] for l in gc_lens] for m in means], dtype=np.float64)
+    cov_lo = np.array([covDist[l][dist.covLowerBoundKey] for l in cov_lens], dtype=np.float64)
+    cov_hi = np.array([covDist[l][dist.covUpperBoundKey] for l in cov_lens], dtype=np.float64)
+    keep = (u_sig, c_sig, u_gc, u_cov, c_gc, c_cov, u_tdb, u_gcl, u_covl, c_gcm, gc_lo, gc_hi, cov_lo, cov_hi)
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    inp = _lib.RefineInput(U, B, vp(u_sig), vp(c_sig), vp(u_gc), vp(u_cov), vp(c_gc), vp(c_cov), vp(u_tdb),
+                           vp(u_gcl), vp(u_covl), vp(c_gcm), vp(gc_lo), vp(gc_hi), gc_lo.shape[0], gc_lo.shape[1],
+                           vp(cov_lo), vp(cov_hi), cov_lo.shape[0])
+    return inp, keep
+
+
 class RefineBins(object):
     def __init__(self, bDebug=False):
         self.logger = logging.getLogger()
@@ -51,34 +82,13 @@ class RefineBins(object):
         binId -> Core (iterated in ascending binId order, which is CPython-2.7's order for small ints) or a list."""
         core_list = [cores[k] for k in sorted(cores)] if isinstance(cores, dict) else list(cores)
         U, B = len(unbinnedContigs), len(core_list)
-        dist = Distributions(gcDist, gcDistPer, tdDist, tdDistPer, covDist, covDistPer)
-        u_len = np.array([c.length for c in unbinnedContigs], dtype=np.float64)
-        arr = lambda it, dt=np.float64: np.ascontiguousarray(np.array(list(it), dtype=dt))
-        u_sig = np.ascontiguousarray(np.array([c.tetraSig for c in unbinnedContigs], dtype=np.float64).reshape(U, _lib.NUM_KMERS))
-        c_sig = np.ascontiguousarray(np.array([c.tetraSig for c in core_list], dtype=np.float64).reshape(B, _lib.NUM_KMERS))
-        u_gc, u_cov = arr(c.GC for c in unbinnedContigs), arr(c.coverage for c in unbinnedContigs)
-        c_gc, c_cov = arr(c.GC for c in core_list), arr(c.coverage for c in core_list)
-        td_lens = _sorted_keys(tdDist)
-        u_tdb = np.ascontiguousarray(np.array([tdDist[l][dist.tdKey] for l in td_lens])[nearest_index(td_lens, u_len)])
-        means = _sorted_keys(gcDist)
-        gc_lens = _sorted_keys(gcDist[means[0]])
-        cov_lens = _sorted_keys(covDist)
-        u_gcl, u_covl = nearest_index(gc_lens, u_len), nearest_index(cov_lens, u_len)
-        c_gcm = nearest_index(means, c_gc)
-        gc_lo = np.array([[gcDist[m][l][dist.gcLowerBoundKey] for l in gc_lens] for m in means], dtype=np.float64)
-        gc_hi = np.array([[gcDist[m][l][dist.gcUpperBoundKey] for l in gc_lens] for m in means], dtype=np.float64)
-        cov_lo = np.array([covDist[l][dist.covLowerBoundKey] for l in cov_lens], dtype=np.float64)
-        cov_hi = np.array([covDist[l][dist.covUpperBoundKey] for l in cov_lens], dtype=np.float64)
+        inp, keep = searchInput(unbinnedContigs, core_list, gcDist, gcDistPer, tdDist, tdDistPer, covDist, covDistPer)
         closest = np.full((U, 3), -1, dtype=np.int32)
         mind = np.full((U, 3), 1e9, dtype=np.float64)
         assigned = np.full(U, -1, dtype=np.int32)
         within = np.zeros((U, max(B, 1)), dtype=np.uint8) if want_within else None
         if U:
-            vp = lambda a: None if a is None else a.ctypes.data_as(ctypes.c_void_p)
-            inp = _lib.RefineInput(U, B, vp(u_sig), vp(c_sig), vp(u_gc), vp(u_cov), vp(c_gc), vp(c_cov), vp(u_tdb),
-                                   vp(u_gcl), vp(u_covl), vp(c_gcm), vp(gc_lo), vp(gc_hi), gc_lo.shape[0], gc_lo.shape[1],
-                                   vp(cov_lo), vp(cov_hi), cov_lo.shape[0])
-            out = _lib.RefineOutput(vp(closest), vp(mind), vp(assigned), vp(within))
+            out = _lib.RefineOutput(_lib.ptr(closest), _lib.ptr(mind), _lib.ptr(assigned), _lib.ptr(within))
             _lib.check(_lib.lib().dbb_refine_host(ctypes.byref(inp), ctypes.byref(out)))
         self.coreOrder = [c.binId for c in core_list]
         res = (closest, mind, assigned)

@@ -221,6 +221,22 @@ typedef struct {
 int dbb_refine_dev(const dbb_refine_input* in, const dbb_refine_output* out, void* stream);
 int dbb_refine_host(const dbb_refine_input* in_host, const dbb_refine_output* out_host);
 
+/* ---- "next" row N5: bin-to-bin merge table -- Merge.run, merge.py:96-156 ------------------------------------
+ * The same filtered search with the BINNED contigs as queries: `search.n_unbinned` contigs against the
+ * `search.n_cores` bins (array order = the order merge.py iterates `bins`), own[u] = position of the contig's own
+ * bin.  For every ordered pair of different bins (b1, b2), over the contigs u of b1 (merge.py:101-151):
+ *   table[b1][b2][0..2] = how many are withinDistGC / withinDistCov / witinDistTD of b2 (:112-119),
+ *   table[b1][b2][3..5] = for how many b2 is the closest valid bin (valid = all three predicates, the contig's own
+ *                         bin skipped, :124-145) in GC / TD / coverage space -- the order of merge.py's
+ *                         `distances = [gcDistance, tdDistance, covDistance]` (:140); strict '<', first bin wins ties.
+ * table is int32 [B][B][6], zeroed by the call; the diagonal stays zero.  closest: [U][3] per contig, or NULL. */
+typedef struct {
+  dbb_refine_input search;
+  const int32_t* own;          /* [U], each in [0, B) */
+} dbb_merge_input;
+int dbb_merge_table_dev(const dbb_merge_input* in, int32_t* d_table, int32_t* d_closest, void* stream);
+int dbb_merge_table_host(const dbb_merge_input* in_host, int32_t* table, int32_t* closest);
+
 /* dense [n][136] -> padded [n][DBB_SIG_STRIDE] on device (used after the all-gather) */
 int dbb_pad_signatures_dev(const float* d_dense, int64_t n, float* d_padded, void* stream);
 

@@ -499,6 +499,82 @@ def refine_worker_literal(unbinnedContig, cores, distributions):
 
 
 # ----------------------------------------------------------------------------------------------
+# N5: bin-to-bin merge table -- merge.py:66-156 (statistics of the bins, then every contig of bin 1 against bin 2
+# and against all bins but its own)
+# ----------------------------------------------------------------------------------------------
+
+MERGE_HEADER = ('Src Bin Id\tGC\tCoverage\tDest Bin Id\tGC\tCoverage\tContigs in Src Bin\tWithin GC\tWithin coverage\t'
+                'Within tetra\tClosest GC\tClosest coverage\tClosest tetra\tMerging score\n')          # merge.py:95
+
+
+def merge_table_literal(contigs, distributions, numKmers=NUM_KMERS):
+    """merge.py:66-156 for ``contigs`` in the order merge.py meets them (objects with contigId, length, GC, coverage,
+    tetraSig and binId; binId -1 = unbinned, skipped as :70-71 does).  Bins are visited in order of first appearance
+    (the frozen stand-in for CPython 2.7's dict order).  Returns the text merge.py writes.  Kept as upstream has it:
+    ``distances = [gcDistance, tdDistance, covDistance]`` (:140), so the column headed 'Closest coverage' counts
+    the bins closest in TD space and 'Closest tetra' those closest in coverage."""
+    bins = {}
+    binnedContigs = {}
+    for contig in contigs:
+        binId = contig.binId
+        if binId != -1:
+            binnedContigs.setdefault(binId, []).append(contig)
+            if binId not in bins:
+                bins[binId] = Core(binId, 0, 0, 0, [0] * numKmers)
+            b = bins[binId]
+            b.length += contig.length
+            weight = float(contig.length) / b.length
+            b.GC = contig.GC * weight + b.GC * (1.0 - weight)
+            b.coverage = contig.coverage * weight + b.coverage * (1.0 - weight)
+            for i in range(0, len(b.tetraSig)):
+                b.tetraSig[i] = contig.tetraSig[i] * weight + b.tetraSig[i] * (1.0 - weight)
+    sig_of = dict((k, np.asarray(v.tetraSig, dtype=np.float64)) for k, v in bins.items())
+    out = [MERGE_HEADER]
+    for binId1, bin1 in bins.items():
+        cs = binnedContigs[binId1]
+        for binId2, bin2 in bins.items():
+            if binId1 == binId2:
+                continue
+            out.append('%s\t%.1f\t%.1f\t%s\t%.1f\t%.1f\t%d' % (binId1, bin1.GC * 100, bin1.coverage, binId2, bin2.GC * 100,
+                                                              bin2.coverage, len(cs)))
+            numWithinGC = numWithinCov = numWithinTetra = closestGC = closestCov = closestTetra = 0
+            for contig in cs:
+                tdDistanceQuery = distance(contig.tetraSig, sig_of[binId2])
+                if distributions.withinDistGC(contig, bin2):
+                    numWithinGC += 1
+                if distributions.withinDistCov(contig, bin2):
+                    numWithinCov += 1
+                if distributions.witinDistTD(tdDistanceQuery, contig):
+                    numWithinTetra += 1
+                closestBin = [None] * 3
+                minDistances = [1e9] * 3
+                for binId, b in bins.items():
+                    if binId == binId1:
+                        continue
+                    if not distributions.withinDistGC(contig, b):
+                        continue
+                    if not distributions.withinDistCov(contig, b):
+                        continue
+                    tdDistance = distance(contig.tetraSig, sig_of[binId])
+                    if not distributions.witinDistTD(tdDistance, contig):
+                        continue
+                    distances = [abs(contig.GC - b.GC), tdDistance, abs(contig.coverage - b.coverage)]
+                    for i, d in enumerate(distances):
+                        if d < minDistances[i]:
+                            minDistances[i] = d
+                            closestBin[i] = binId
+                if closestBin[0] == binId2:
+                    closestGC += 1
+                if closestBin[1] == binId2:
+                    closestCov += 1
+                if closestBin[2] == binId2:
+                    closestTetra += 1
+            out.append('\t%d\t%d\t%d\t%d\t%d\t%d' % (numWithinGC, numWithinCov, numWithinTetra, closestGC, closestCov, closestTetra))
+            out.append('\t%.2f\n' % (float(closestGC + closestCov + closestTetra) / (3 * len(cs))))
+    return ''.join(out)
+
+
+# ----------------------------------------------------------------------------------------------
 # N2: sequence side of preprocess -- splitScaffolds.py:27-53, seqUtils.py:258-265,
 # preprocess.py:94-100, :118-161 (what a worker computes from the sequence alone)
 # ----------------------------------------------------------------------------------------------

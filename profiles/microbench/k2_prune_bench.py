@@ -25,8 +25,11 @@ else:
 dt = device.DevicePairTables(t)
 
 
-def timed(fn, reps=3):
-    for _ in range(2): r = fn()
+REPS = int(sys.argv[4]) if len(sys.argv) > 4 else 3
+
+
+def timed(fn, reps=REPS):
+    for _ in range(1 if REPS == 1 else 2): r = fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

@@ -1,0 +1,115 @@
+"""N5 row: the bin-to-bin merge table (merge.py) against the reference's own output files (golden) and the oracle's
+literal loop."""
+import ast
+import os
+
+import numpy as np
+import pytest
+
+from oracle import dbb_oracle as O
+from tests.test_oracle_golden import merge_case
+
+pytestmark = pytest.mark.gpu
+
+
+def _write_inputs(d, contigs, gcDist, tdDist, covDist):
+    from dbb_b200.genomicSignatures import GenomicSignatures
+    with open(os.path.join(d, 'contigs.seq_stats.tsv'), 'w') as f:
+        f.write('Contig Id\tLength\tGC\tCoverage\n')
+        for c in contigs:
+            f.write('%s\t%d\t%r\t%r\n' % (c.contigId, c.length, c.GC, c.coverage))
+    with open(os.path.join(d, 'contigs.tetra.tsv'), 'w') as f:
+        f.write('Contig Id\t' + '\t'.join(GenomicSignatures(4, 1).canonicalKmerOrder()) + '\n')
+        for c in contigs:
+            f.write(c.contigId + '\t' + '\t'.join(repr(float(x)) for x in c.tetraSig) + '\n')
+    with open(os.path.join(d, 'bins.tsv'), 'w') as f:
+        f.write('# parameters\nContig Id\tBin Id\tLength\n')
+        for c in contigs:
+            f.write('%s\t%s\t%d\n' % (c.contigId, 'unbinned' if c.binId == -1 else c.binId, c.length))
+    data = os.path.join(d, 'data')
+    os.makedirs(data)
+    plain = lambda t: dict((k, plain(v)) for k, v in t.items()) if isinstance(t, dict) else t
+    for name, t in (('gc_dist.txt', gcDist), ('td_dist.txt', tdDist)):
+        with open(os.path.join(data, name), 'w') as f:
+            f.write(repr(plain(t)))
+    with open(os.path.join(d, 'coverage_dist.txt'), 'w') as f:
+        f.write(repr(plain(covDist)))
+    return data
+
+
+def test_merge_run_writes_the_reference_file(tmp_path):
+    """Merge.run through real files (the reference's call, merge.py:35) == the file the reference's own Merge.run wrote."""
+    from dbb_b200.merge import Merge
+    for tag in 'abc':
+        g, contigs, pers, gcDist, td, covDist = merge_case(tag)
+        d = str(tmp_path / tag)
+        os.makedirs(d)
+        data = _write_inputs(d, contigs, gcDist, td, covDist)
+        assert ast.literal_eval(open(os.path.join(data, 'td_dist.txt')).read()) == dict((k, dict(v)) for k, v in td.items())
+        out = os.path.join(d, 'merge.tsv')
+        Merge().run(d, os.path.join(d, 'bins.tsv'), pers[0], pers[1], pers[2], out, dataDir=data)
+        assert open(out).read() == str(g[tag + '_merge_tsv']), tag
+    with pytest.raises(SystemExit):
+        Merge().run(str(tmp_path / 'missing'), 'x', 99, 99, 99, 'y')
+
+
+def test_merge_table_random_instance_vs_literal_loop():
+    """700 binned contigs, 5 genomes cut into 15 bins, mixed percentiles; per-contig closest bins and the whole table
+    against the literal loop; a bin with a single contig and exact ties (two bins with identical statistics: the one
+    visited first must win) are planted."""
+    from dbb_b200 import synthetic
+    from dbb_b200.data import load_td_dist
+    from dbb_b200.genomicSignatures import GenomicSignatures
+    from dbb_b200.merge import Merge
+    n = 700
+    meta = synthetic.make_metagenome(seed=51, n_scaffolds=n, min_len=1500, max_len=25000, n_genomes=5)
+    seqs = synthetic.generate_sequences(meta)
+    counts, _ = GenomicSignatures(4, 1).signatures(seqs, want_freq=False)
+    sig = counts.astype(np.float64) / counts.sum(axis=1, keepdims=True)
+    rng = np.random.RandomState(51)
+    bin_of = meta.genome.astype(np.int64) * 3 + rng.randint(0, 3, size=n)
+    moved = rng.rand(n) < 0.1
+    bin_of[moved] = rng.randint(0, 15, size=int(moved.sum()))
+    td = load_td_dist()
+    gcDist, covDist = synthetic.synthetic_gc_dist(sorted(td.keys())), synthetic.synthetic_cov_dist(seed=7)
+    contigs = []
+    for i in range(n):
+        c = O.Contig('c%d' % i, int(meta.length[i]), float(meta.gc_obs[i]), float(meta.coverage[i]), sig[i])
+        c.binId = 'bin%d' % bin_of[i]
+        contigs.append(c)
+    # bin15: one contig; bin16 / bin17: twins of each other (same single member statistics -> exact ties everywhere)
+    for b, src in ((15, contigs[10]), (16, contigs[3]), (17, contigs[3])):
+        c = O.Contig('x%d' % b, src.length, src.GC, src.coverage, src.tetraSig.copy())
+        c.binId = 'bin%d' % b
+        contigs.append(c)
+    m = Merge()
+    bins, table, closest = m.mergeTable(contigs, gcDist, 95, td, 90, covDist, 99, want_closest=True)
+    dist = O.Distributions(gcDist, 95, td, 90, covDist, 99)
+    assert m.formatTable(bins, table) == O.merge_table_literal(contigs, dist)
+    assert len(bins) == 18 and np.all(table[np.arange(18), np.arange(18)] == 0)
+    pos = dict((b.binId, k) for k, b in enumerate(bins))
+    # ties: wherever one twin is the closest bin of a contig outside both, it is the twin visited first
+    first, second = sorted((pos['bin16'], pos['bin17']))
+    outside = np.array([pos[c.binId] not in (first, second) for c in contigs])
+    assert not np.any(closest[outside] == second) and np.any(closest[outside] == first)
+    # per-contig closest bins against the N1 oracle with the own bin removed
+    cores = dict((k, b) for k, b in enumerate(bins))
+    for u in range(0, len(contigs), 7):
+        own = pos[contigs[u].binId]
+        cb, _, _, _, _, _ = O.refine_worker_literal(contigs[u], dict((k, b) for k, b in cores.items() if k != own), dist)
+        assert [(-1 if x is None else x) for x in cb] == closest[u].tolist()
+
+
+def test_merge_table_degenerate_inputs():
+    from dbb_b200 import synthetic
+    from dbb_b200.data import load_td_dist
+    from dbb_b200.merge import Merge
+    td = load_td_dist()
+    gcDist, covDist = synthetic.synthetic_gc_dist(sorted(td.keys())), synthetic.synthetic_cov_dist(seed=7)
+    bins, table = Merge().mergeTable([], gcDist, 99, td, 99, covDist, 99)
+    assert bins == [] and table.shape == (0, 0, 6)
+    c = O.Contig('a', 5000, 0.5, 10.0, np.full(136, 1 / 136.0))
+    c.binId = 'only'
+    bins, table = Merge().mergeTable([c], gcDist, 99, td, 99, covDist, 99)
+    assert len(bins) == 1 and table.tolist() == [[[0] * 6]]
+    assert Merge().formatTable(bins, table) == O.MERGE_HEADER

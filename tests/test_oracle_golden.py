@@ -193,3 +193,31 @@ def test_greedy_oracle_matches_reference_outputs():
         g, contigs, per, minBin, gcDist, tdDist, covDist = greedy_case(tag)
         cores = O.greedy_literal(contigs, minBin, O.Distributions(gcDist, per, tdDist, per, covDist, per))
         check_greedy_against_golden(g, tag, contigs, cores)
+
+
+def merge_case(tag):
+    """(golden, contigs in file order with binId set, (gcPer, tdPer, covPer), gcDist, tdDist, covDist) of the N5 golden
+    vectors (tests/golden/make_golden_merge.py)."""
+    from dbb_b200 import synthetic
+    from dbb_b200.data import load_td_dist
+    g = util.golden_npz('ref_merge.npz')
+    td = load_td_dist()
+    gcDist, covDist = synthetic.synthetic_gc_dist(sorted(td.keys())), synthetic.synthetic_cov_dist(seed=7)
+    contigs = []
+    for i in range(len(g[tag + '_length'])):
+        c = O.Contig('c%d' % i, int(g[tag + '_length'][i]), float(g[tag + '_gc'][i]), float(g[tag + '_cov'][i]), g[tag + '_sig'][i])
+        b = str(g[tag + '_bin'][i])
+        c.binId = -1 if b == 'unbinned' else b
+        contigs.append(c)
+    return g, contigs, [int(x) for x in g[tag + '_pers']], gcDist, td, covDist
+
+
+def test_merge_oracle_matches_reference_outputs():
+    """N5 row: the literal restatement of merge.py:66-156 writes, byte for byte, the file the reference's own Merge.run
+    wrote (three cases; in case c every genome is cut into three bins, so the three 'closest' columns differ)."""
+    for tag in 'abc':
+        g, contigs, pers, gcDist, td, covDist = merge_case(tag)
+        dist = O.Distributions(gcDist, pers[0], td, pers[1], covDist, pers[2])
+        assert O.merge_table_literal(contigs, dist) == str(g[tag + '_merge_tsv']), tag
+    rows = [r.split('\t') for r in str(g['c_merge_tsv']).strip().split('\n')[1:]]
+    assert any(r[10] != r[11] or r[11] != r[12] for r in rows)
