@@ -53,6 +53,19 @@ class GreedyInput(ctypes.Structure):
                 ('gc_nm', c_i32), ('gc_nl', c_i32), ('cov_lo', c_vp), ('cov_hi', c_vp), ('cov_nl', c_i32)]
 
 
+class PruneInput(ctypes.Structure):
+    _fields_ = [('n', c_i64), ('sig', c_vp), ('weights', c_vp), ('cls', c_vp), ('length', c_vp), ('td_bound', c_vp),
+                ('gc', c_vp), ('gc_mbin', c_vp), ('gc_lbin', c_vp), ('cov', c_vp), ('cov_lbin', c_vp),
+                ('row0', c_i64), ('row1', c_i64), ('rank', c_i32), ('world', c_i32), ('margin', ctypes.c_float)]
+
+
+class PruneBuffers(ctypes.Structure):
+    _fields_ = [('sig_sorted', c_vp), ('length', c_vp), ('td_bound', c_vp), ('gc', c_vp), ('gc_mbin', c_vp),
+                ('gc_lbin', c_vp), ('cov', c_vp), ('cov_lbin', c_vp), ('col_id', c_vp), ('p_sorted', c_vp),
+                ('item_order', c_vp), ('tile_off', c_vp), ('tile_list', c_vp), ('tile_count', c_vp), ('mine', c_vp),
+                ('info', c_vp), ('scratch', c_vp), ('scratch_bytes', c_i64)]
+
+
 class MergeInput(ctypes.Structure):
     _fields_ = [('search', RefineInput), ('own', c_vp)]
 
@@ -83,6 +96,10 @@ SIGNATURES = {
     'dbb_pairs_scratch_bytes': (c_i64, [c_i64, c_i64, c_i32]),
     'dbb_pairs_launches': (ctypes.c_int, [c_i64, c_i64]),
     'dbb_pairs_host': (ctypes.c_int, [ctypes.POINTER(PairsInput), c_i64, c_i64, ctypes.POINTER(PairsOutput)]),
+    'dbb_prune_scratch_bytes': (c_i64, [c_i64, c_i64, c_i32]),
+    'dbb_prune_plan_dev': (ctypes.c_int, [ctypes.POINTER(PruneInput), ctypes.POINTER(PruneBuffers), c_vp]),
+    'dbb_prune_second_dev': (ctypes.c_int, [ctypes.POINTER(PruneInput), ctypes.POINTER(PruneBuffers), c_vp, c_i64, c_vp]),
+    'dbb_prune_merge_dev': (ctypes.c_int, [ctypes.POINTER(PruneBuffers), c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'dbb_refine_dev': (ctypes.c_int, [ctypes.POINTER(RefineInput), ctypes.POINTER(RefineOutput), c_vp]),
     'dbb_refine_host': (ctypes.c_int, [ctypes.POINTER(RefineInput), ctypes.POINTER(RefineOutput)]),
     'dbb_merge_table_dev': (ctypes.c_int, [ctypes.POINTER(MergeInput), c_vp, c_vp, c_vp]),

@@ -200,8 +200,11 @@ def projection_weights(device):
         names, _ = _lib.kmer_table()
         w = np.zeros(_lib.SIG_STRIDE, dtype=np.float32)
         w[:_lib.NUM_KMERS] = [min(1.0, max(0.0, (sum(ch in 'GC' for ch in nm) - 1) / 2.0)) for nm in names]
-        _GC_WEIGHTS = w
-    return torch.from_numpy(_GC_WEIGHTS).to(device)
+        _GC_WEIGHTS = {None: w}
+    key = str(device)
+    if key not in _GC_WEIGHTS:                                         # uploaded once per device
+        _GC_WEIGHTS[key] = torch.from_numpy(_GC_WEIGHTS[None]).to(device)
+    return _GC_WEIGHTS[key]
 
 
 class _SortedTables(object):
@@ -225,8 +228,9 @@ def pairs_pruned(sig_padded, dt, row0=0, row1=None, k=0, topk_filter=0, want_cou
     part=(rank, world): multi-GPU -- the row tiles of the sorted order are dealt to the ranks by decreasing work (their
     tile lists differ in length by an order of magnitude, contiguous blocks would not balance); the rank's results are
     returned for its rows only.  Otherwise [row0, row1) are positions in the sorted order.  The dict carries ``row_ids``,
-    the original ids of the returned rows, and ``tiles_visited`` / ``tiles_total``.  Planning (projection, sort,
-    gathers, tile mask) uses torch ops on the device; the distance work is the same pairs_kernel."""
+    the original ids of the returned rows, and ``tiles_visited`` / ``tiles_total``.  Planning (projection, sort, gathers,
+    tile lists, list merge) is csrc/prune.cu (``dbb_prune_plan_dev`` / ``_second_dev`` / ``_merge_dev``), enqueued on the
+    same stream with a single host read (the list sizes); the distance work is the same pairs_kernel."""
     require_cuda()
     if metric != 'l1':
         raise ValueError('pairs_pruned: the projection bound is for the Manhattan distance')
@@ -247,108 +251,54 @@ def pairs_pruned(sig_padded, dt, row0=0, row1=None, k=0, topk_filter=0, want_cou
             marks.append((name, e))
 
     mark('start')
-    p = torch.mv(sig_padded, projection_weights(dev))
-    key = p
+    world = part[1] if part is not None else 1
+    rank = part[0] if part is not None else 0
+    cls = None
     if dt.td_bound is not None and n_classes > 1:
         cls = getattr(dt, '_prune_class', None)
         if cls is None or cls.shape[0] != n or getattr(dt, '_prune_nc', 0) != n_classes:
-            rank = torch.empty(n, dtype=torch.int64, device=dev)
-            rank[torch.argsort(dt.td_bound, stable=True)] = torch.arange(n, device=dev)
-            cls = ((rank * n_classes) // max(n, 1)).to(torch.float32)
+            # once per table set (not per sweep): equal-count classes of the per-scaffold TD bound
+            order = torch.empty(n, dtype=torch.int64, device=dev)
+            order[torch.argsort(dt.td_bound, stable=True)] = torch.arange(n, device=dev)
+            cls = ((order * n_classes) // max(n, 1)).to(torch.float32)
             dt._prune_class, dt._prune_nc = cls, n_classes
-        key = cls * 4.0 + p.clamp(0.0, 1.0)                        # p is in [0, 1]: classes do not interleave
-    perm = torch.argsort(key, stable=True)
-    p_s = p[perm]
-    sig_s = sig_padded.index_select(0, perm)
-    st = _SortedTables()
-    st.n = n
-    for name in ('length', 'td_bound', 'gc', 'gc_mbin', 'gc_lbin', 'cov', 'cov_lbin'):
-        a = getattr(dt, name)
-        setattr(st, name, None if a is None else a.index_select(0, perm))
-    st.gc_lo, st.gc_hi, st.cov_lo, st.cov_hi = dt.gc_lo, dt.gc_hi, dt.cov_lo, dt.cov_hi
-    n_ct = (n + T - 1) // T
-    n_rt = (row1 - row0 + T - 1) // T
-    pad = n_ct * T - n
-    p_pad = torch.cat([p_s, p_s[-1:].expand(pad)]) if pad else p_s
-    pmin_c, pmax_c = p_pad.view(n_ct, T).amin(1), p_pad.view(n_ct, T).amax(1)
-    p_rows = p_s[row0:row1]
-    rows_pad0 = n_rt * T - (row1 - row0)
-    if rows_pad0:
-        p_rows = torch.cat([p_rows, p_rows[-1:].expand(rows_pad0)])
-    pmin_r, pmax_r = p_rows.view(n_rt, T).amin(1), p_rows.view(n_rt, T).amax(1)
-    gap = torch.maximum(pmin_c[None, :] - pmax_r[:, None], pmin_r[:, None] - pmax_c[None, :]).clamp_(min=0)
-    lb = 2.0 * gap - margin                                   # lower bound of every distance in the tile pair
-    if st.td_bound is not None:
-        tdb_pad = torch.cat([st.td_bound, st.td_bound.new_full((pad,), float('-inf'))]) if pad else st.td_bound
-        tmax_c = tdb_pad.view(n_ct, T).amax(1)
-        rows_pad = n_rt * T - (row1 - row0)
-        tdb_rows = st.td_bound[row0:row1]
-        if rows_pad:
-            tdb_rows = torch.cat([tdb_rows, tdb_rows.new_full((rows_pad,), float('-inf'))])
-        tmax_r = tdb_rows.view(n_rt, T).amax(1)
-        need = lb <= torch.maximum(tmax_r[:, None], tmax_c[None, :])
-    else:
-        need = lb <= 0
-    col_id = perm.to(torch.int32)
-    mine = None
-    if part is not None:
-        rank, world = part
-        by_work = torch.argsort(need.sum(1), descending=True, stable=True)
-        mine = torch.zeros(n_rt, dtype=torch.bool, device=dev)
-        mine[by_work[rank::world]] = True
-        need = need & mine[:, None]
+    b = _prune_buffers(dt, n, row0, row1, world, dev)
+    st = b.st
+    L = _lib.lib()
+    inp = _lib.PruneInput(n, _p(sig_padded), _p(projection_weights(dev)), _p(cls), _p(dt.length), _p(dt.td_bound), _p(dt.gc),
+                          _p(dt.gc_mbin), _p(dt.gc_lbin), _p(dt.cov), _p(dt.cov_lbin), row0, row1, rank, world, float(margin))
+    _lib.check(L.dbb_prune_plan_dev(ctypes.byref(inp), ctypes.byref(b.struct), _stream()))
+    n_rt, n_ct = b.n_rt, b.n_ct
+    n_mine = len(range(rank, n_rt, world))
 
-    def lists(mask, active=None, target=_ITEMS_TARGET):
-        # every row tile visits its tiles nearest (smallest lower bound) first: the top-k threshold tightens at once
-        # and the far tiles add next to nothing (in ascending tile order every tile would bring better candidates
-        # than the one before -- the worst case for a streaming top-k)
-        cnt = mask.sum(1)
-        off = torch.zeros(n_rt + 1, dtype=torch.int64, device=dev)
-        off[1:] = torch.cumsum(cnt, 0)
-        key = torch.where(mask, lb, torch.full_like(lb, float('inf')))
-        by_lb = torch.argsort(key, dim=1, stable=True)
-        keep = torch.arange(n_ct, device=dev)[None, :] < cnt[:, None]
-        tl = by_lb[keep].to(torch.int32).contiguous()
-        order = torch.argsort(cnt, descending=True, stable=True).to(torch.int32)   # most work first; empty lists last
+    def split_for(n_act, target):
         # ~5 work items per SM: the lists differ in length by an order of magnitude, whole row tiles do not balance,
         # but every extra segment refills its own top-k lists
-        n_act = n_rt if active is None else active
-        split = int(min(8, max(1, -(-target // max(n_act, 1)))))
-        return (col_id, order, off, tl, split, 0 if active is None else active), int(off[-1].item())
+        return int(min(8, max(1, -(-target // max(n_act, 1)))))
 
-    sp, visited = lists(need, active=None if mine is None else int(mine.sum().item()))
+    sp = (b.col_id, b.order, b.off, b.tl, split_for(n_mine, _ITEMS_TARGET), 0 if part is None else n_mine)
     mark('plan')
-    res = pairs(sig_s, st, row0, row1, k=k, topk_filter=topk_filter, want_count=want_count, metric=metric, sparse=sp)
+    res = pairs(b.sig, st, row0, row1, k=k, topk_filter=topk_filter, want_count=want_count, metric=metric, sparse=sp)
     mark('sweep')
-    visited1 = visited
-    if k > 0 and not (topk_filter & FILTER_TD):
-        # unfiltered (or GC / coverage filtered) top-k: candidates may sit beyond the TD window
-        thr = res['dist'][:, k - 1]
-        rows_pad = n_rt * T - (row1 - row0)
-        if rows_pad:
-            thr = torch.cat([thr, thr.new_full((rows_pad,), float('-inf'))])
-        t_r = thr.view(n_rt, T).amax(1)
-        more = (lb <= t_r[:, None]) & ~need
-        if mine is not None:
-            more = more & mine[:, None]
-        n_aff = int(more.any(1).sum().item())
+    launches = (10 if world > 1 else 9) + 2                       # planner kernels + pairs_kernel + merge_kernel
+    second = k > 0 and not (topk_filter & FILTER_TD)
+    if second:
+        # unfiltered (or GC / coverage filtered) top-k: candidates may sit beyond the TD window.  Only the affected row
+        # tiles run again (they sort first: the others have empty lists); their rows' lists are merged with the first
+        # sweep's in the (distance, id) order
+        kth = res['dist'][:, k - 1]
+        _lib.check(L.dbb_prune_second_dev(ctypes.byref(inp), ctypes.byref(b.struct), _p(kth), k, _stream()))
+        launches += 6
+    info = b.info.cpu().tolist()                                   # the one host read: list sizes of both plans
+    visited1, visited, n_aff = info[0], info[0], 0
+    if second:
+        visited, n_aff = info[0] + info[2], info[3]
         if n_aff:
-            # only the affected row tiles run again (they sort first: the others have empty lists); their rows' lists
-            # are merged with the first sweep's in the (distance, id) order
-            sp2, v2 = lists(more, active=n_aff, target=2 * _ITEMS_TARGET)     # few row tiles, short lists: cut finer
-            visited += v2
-            r2 = pairs(sig_s, st, row0, row1, k=k, topk_filter=topk_filter, want_count=False, metric=metric, sparse=sp2)
-            aff = sp2[1][:n_aff].to(torch.int64)
-            rows_aff = (aff[:, None] * T + torch.arange(T, device=dev)[None, :]).flatten()
-            rows_aff = rows_aff[rows_aff < (row1 - row0)]
-            d = torch.cat([res['dist'][rows_aff], r2['dist'][rows_aff]], 1)
-            j = torch.cat([res['idx'][rows_aff], r2['idx'][rows_aff]], 1)
-            jkey = torch.where(j < 0, torch.full_like(j, 2 ** 31 - 1), j)
-            o1 = torch.argsort(jkey, dim=1, stable=True)
-            d, j = d.gather(1, o1), j.gather(1, o1)
-            o2 = torch.argsort(d, dim=1, stable=True)[:, :k]
-            res['dist'][rows_aff] = d.gather(1, o2)
-            res['idx'][rows_aff] = j.gather(1, o2)
+            sp2 = (b.col_id, b.order, b.off, b.tl, split_for(n_aff, 2 * _ITEMS_TARGET), n_aff)   # few row tiles, short lists: cut finer
+            r2 = pairs(b.sig, st, row0, row1, k=k, topk_filter=topk_filter, want_count=False, metric=metric, sparse=sp2)
+            _lib.check(L.dbb_prune_merge_dev(ctypes.byref(b.struct), row1 - row0, k, _p(res['idx']), _p(res['dist']),
+                                             _p(r2['idx']), _p(r2['dist']), _stream()))
+            launches += 3
     mark('second sweep + merge')
     if isinstance(timings, list):
         timings.append(marks)                      # events only; the caller reads them after its own synchronisation
@@ -357,18 +307,61 @@ def pairs_pruned(sig_padded, dt, row0=0, row1=None, k=0, topk_filter=0, want_cou
         for (_, e0), (name, e1) in zip(marks, marks[1:]):
             timings[name] = e0.elapsed_time(e1)
         timings['tiles_first'], timings['tiles_second'] = visited1, visited - visited1
-    if mine is None:
-        res['row_ids'] = perm[row0:row1]
+    if part is None:
+        res['row_ids'] = b.col_id[row0:row1].to(torch.int64)
     else:
-        rows_mine = (mine.nonzero()[:, 0][:, None] * T + torch.arange(T, device=dev)[None, :]).flatten()
+        rows_mine = (b.mine.nonzero()[:, 0][:, None] * T + torch.arange(T, device=dev)[None, :]).flatten()
         rows_mine = rows_mine[rows_mine < n]
         for key_ in ('idx', 'dist', 'count', 'neighbour_bp'):
             if key_ in res:
                 res[key_] = res[key_][rows_mine]
-        res['row_ids'] = perm[rows_mine]
-    res['tiles_visited'], res['tiles_total'] = visited, (n_rt if mine is None else int(mine.sum().item())) * n_ct
-    res['launches'] = 2 if visited == visited1 else 4            # pairs_kernel + merge_kernel per sweep
+        res['row_ids'] = b.col_id[rows_mine].to(torch.int64)
+    res['tiles_visited'], res['tiles_total'] = visited, n_mine * n_ct
+    res['launches'] = launches
     return res
+
+
+class _PruneBuffers(object):
+    pass
+
+
+def _prune_buffers(dt, n, row0, row1, world, dev):
+    """Device buffers of the planner (csrc/prune.cu) for one problem shape, kept on the table object between sweeps:
+    the sorted signature matrix and tables, the tile lists and the planner's scratch."""
+    key = (n, row0, row1, world, str(dev))
+    b = getattr(dt, '_prune_buf', None)
+    if b is not None and b.key == key:
+        return b
+    rows = row1 - row0
+    b = _PruneBuffers()
+    b.key = key
+    b.n_ct, b.n_rt = (n + 127) // 128, (rows + 127) // 128
+    n_slots = -(-b.n_rt // world) if world > 1 else b.n_rt
+    b.sig = torch.empty((n, _lib.SIG_STRIDE), dtype=torch.float32, device=dev)
+    st = _SortedTables()
+    st.n = n
+    for name in ('length', 'td_bound', 'gc', 'gc_mbin', 'gc_lbin', 'cov', 'cov_lbin'):
+        a = getattr(dt, name)
+        setattr(st, name, None if a is None else torch.empty_like(a))
+    st.gc_lo, st.gc_hi, st.cov_lo, st.cov_hi = dt.gc_lo, dt.gc_hi, dt.cov_lo, dt.cov_hi
+    b.st = st
+    b.col_id = torch.empty(n, dtype=torch.int32, device=dev)
+    b.p = torch.empty(n, dtype=torch.float32, device=dev)
+    b.order = torch.empty(b.n_rt, dtype=torch.int32, device=dev)
+    b.off = torch.empty(b.n_rt + 1, dtype=torch.int64, device=dev)
+    b.tl = torch.empty(max(n_slots * b.n_ct, 1), dtype=torch.int32, device=dev)
+    b.cnt = torch.empty(b.n_rt, dtype=torch.int32, device=dev)
+    b.mine = torch.zeros(b.n_rt, dtype=torch.uint8, device=dev)
+    b.info = torch.zeros(4, dtype=torch.int64, device=dev)
+    nbytes = int(_lib.lib().dbb_prune_scratch_bytes(n, rows, world))
+    if nbytes < 0:
+        _lib.check(-1)
+    b.scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    b.struct = _lib.PruneBuffers(_p(b.sig), _p(st.length), _p(st.td_bound), _p(st.gc), _p(st.gc_mbin), _p(st.gc_lbin), _p(st.cov),
+                                 _p(st.cov_lbin), _p(b.col_id), _p(b.p), _p(b.order), _p(b.off), _p(b.tl), _p(b.cnt), _p(b.mine),
+                                 _p(b.info), _p(b.scratch), nbytes)
+    dt._prune_buf = b
+    return b
 
 
 def unsort_rows(res, n):

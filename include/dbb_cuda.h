@@ -191,6 +191,51 @@ int dbb_pairs_launches(int64_t n, int64_t rows);
 int dbb_pairs_host(const dbb_pairs_input* in_host, int64_t row0, int64_t row1,
                    const dbb_pairs_output* out_host);
 
+/* ---- planner of the exact pruned sweep (the sparse sweep of dbb_pairs_input, built on the device) -------------
+ * Sorts the scaffolds by (class, p = <sig, weights>), carries the signature rows and per-scaffold tables into that
+ * order, and writes the tile lists dbb_pairs_dev takes: a (row tile, column tile) pair is visited iff
+ * 2 * gap(p intervals) - margin <= max(largest td_bound of the row tile, of the column tile)  [no td_bound: <= 0].
+ * Exact for any weights in [0, 1] because signatures sum to 1: L1(a, b) >= 2 |p_a - p_b|.  Lists are ordered
+ * nearest tile first.  world > 1: the row tiles are dealt to the ranks by decreasing list length; a rank's lists
+ * cover its own row tiles only (mine[t] = 1).  All pointers are device pointers, caller-allocated. */
+typedef struct {
+  int64_t n;
+  const float* sig;            /* [n][DBB_SIG_STRIDE] */
+  const float* weights;        /* [DBB_SIG_STRIDE], in [0, 1], padding columns 0 */
+  const float* cls;            /* [n] sort class 0, 1, 2, ... as float (e.g. quantile of td_bound), or NULL */
+  const int32_t* length; const float* td_bound; const double* gc; const int32_t* gc_mbin; const int32_t* gc_lbin;
+  const double* cov; const int32_t* cov_lbin;     /* [n] each; NULL = absent */
+  int64_t row0, row1;          /* rows of the SORTED order the sweep will cover */
+  int32_t rank, world;         /* world <= 1: single GPU; else row0 = 0, row1 = n */
+  float margin;                /* slack of the FP32 projection, e.g. 1e-5 */
+} dbb_prune_input;
+
+typedef struct {
+  float* sig_sorted;           /* [n][DBB_SIG_STRIDE] */
+  int32_t* length; float* td_bound; double* gc; int32_t* gc_mbin; int32_t* gc_lbin; double* cov; int32_t* cov_lbin;
+  int32_t* col_id;             /* [n] original index of sorted position j */
+  float* p_sorted;             /* [n] */
+  int32_t* item_order;         /* [row tiles] by decreasing list length */
+  int64_t* tile_off;           /* [row tiles + 1] */
+  int32_t* tile_list;          /* capacity: row tiles of this rank x column tiles */
+  int32_t* tile_count;         /* [row tiles] */
+  uint8_t* mine;               /* [row tiles] */
+  int64_t* info;               /* [4]: tiles listed, row tiles with a non-empty list -- first plan, second plan */
+  void* scratch; int64_t scratch_bytes;   /* dbb_prune_scratch_bytes; must be left alone between the plan calls */
+} dbb_prune_buffers;
+
+int64_t dbb_prune_scratch_bytes(int64_t n, int64_t rows, int32_t world);
+int dbb_prune_plan_dev(const dbb_prune_input* in, const dbb_prune_buffers* buf, void* stream);
+/* Unfiltered top-k: after the first sweep, the tiles not yet visited whose lower bound does not exceed the largest
+ * k-th best distance (d_kth[row * kth_stride], row relative to row0) of the row tile.  Overwrites item_order /
+ * tile_off / tile_list / tile_count (the affected row tiles sort first; info[3] = how many).  Same `in` as the plan. */
+int dbb_prune_second_dev(const dbb_prune_input* in, const dbb_prune_buffers* buf, const float* d_kth, int64_t kth_stride,
+                         void* stream);
+/* Merges the second sweep's top-k lists into the first sweep's for the rows of the affected row tiles, in the
+ * (distance, id) order of dbb_pairs_output ([rows][k] each, ids as written by dbb_pairs_dev, -1 padding). */
+int dbb_prune_merge_dev(const dbb_prune_buffers* buf, int64_t rows, int32_t k, int32_t* d_idx1, float* d_dist1,
+                        const int32_t* d_idx2, const float* d_dist2, void* stream);
+
 /* ---- "next" row N1: rectangular filtered nearest-core search -- refineBins.py:42-96 (__workerThread), the same
  * ---- loop in unbinned.py:156-176.  For every unbinned contig u over all cores c (in array order):
  * valid(u,c) = withinDistGC(u,c) && withinDistCov(u,c) && L1(u,c) < boundDistTD(u) (distributions.py:75-127 with
