@@ -70,6 +70,10 @@ class MergeInput(ctypes.Structure):
     _fields_ = [('search', RefineInput), ('own', c_vp)]
 
 
+class UnbinnedInput(ctypes.Structure):
+    _fields_ = [('search', RefineInput), ('group', c_vp), ('n_groups', c_i64)]
+
+
 class RefineOutput(ctypes.Structure):
     _fields_ = [('closest', c_vp), ('min_dist', c_vp), ('assigned', c_vp), ('within', c_vp)]
 
@@ -104,6 +108,8 @@ SIGNATURES = {
     'dbb_refine_host': (ctypes.c_int, [ctypes.POINTER(RefineInput), ctypes.POINTER(RefineOutput)]),
     'dbb_merge_table_dev': (ctypes.c_int, [ctypes.POINTER(MergeInput), c_vp, c_vp, c_vp]),
     'dbb_merge_table_host': (ctypes.c_int, [ctypes.POINTER(MergeInput), c_vp, c_vp]),
+    'dbb_unbinned_table_dev': (ctypes.c_int, [ctypes.POINTER(UnbinnedInput), c_vp, c_vp]),
+    'dbb_unbinned_table_host': (ctypes.c_int, [ctypes.POINTER(UnbinnedInput), c_vp]),
     'dbb_greedy_host': (ctypes.c_int, [ctypes.POINTER(GreedyInput), c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'dbb_pca_gram_host': (ctypes.c_int, [c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp]),
     'dbb_pca_project_host': (ctypes.c_int, [c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_i32, c_vp]),

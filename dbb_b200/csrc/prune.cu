@@ -192,13 +192,17 @@ struct Stats {
 
 // lower bound of every distance between row tile rt and column tile ct, and whether this plan visits the pair
 __device__ __forceinline__ bool visit(const Stats& S, int rt, int ct, float pmin_r, float pmax_r, float bound_r, float thr, float* lb_out) {
-  const float gap = fmaxf(fmaxf(__ldg(S.pmin_c + ct) - pmax_r, pmin_r - __ldg(S.pmax_c + ct)), 0.f);
+  const float cmin = __ldg(S.pmin_c + ct), cmax = __ldg(S.pmax_c + ct);
+  const float gap = fmaxf(fmaxf(cmin - pmax_r, pmin_r - cmax), 0.f);
   const float lb = 2.f * gap - S.margin;
   *lb_out = lb;
+  // a tile whose rows are all NaN signatures has an empty interval: no finite distance in the pair
+  const bool empty = !(pmin_r <= pmax_r) || !(cmin <= cmax);
   // the tile that holds the row tile's own first row is always taken: every processed row tile then writes its
   // outputs, also one whose rows are all NaN signatures
-  const bool first = (S.has_td ? lb <= fmaxf(bound_r, __ldg(S.tmax_c + ct)) : lb <= 0.f) || ct == (int)((S.row0 + (int64_t)rt * T) / T);
-  return S.second ? (lb <= thr && !first) : first;
+  const bool diag = ct == (int)((S.row0 + (int64_t)rt * T) / T);
+  const bool first = diag || (!empty && (S.has_td ? lb <= fmaxf(bound_r, __ldg(S.tmax_c + ct)) : lb <= 0.f));
+  return S.second ? (!empty && lb <= thr && !first) : first;
 }
 
 __global__ void __launch_bounds__(256) count_kernel(Stats S, const uint8_t* __restrict__ mine, int32_t* __restrict__ cnt) {

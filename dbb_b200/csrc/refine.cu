@@ -19,10 +19,14 @@ namespace {
 struct RefineParams {
   dbb_refine_input in;
   dbb_refine_output out;
-  // N5 (merge.py:96-156): the queries are binned contigs; own[u] is skipped by the closest-bin search and the
-  // per-pair flags / closest bins are tallied per (own bin, other bin)
-  const int32_t* own;
-  int32_t* table;                // [B][B][6] or nullptr
+  // N5 (merge.py:96-156): the queries are binned contigs; exclude[u] (the own bin) is skipped by the closest-bin search
+  // and the per-pair flags / closest bins are tallied per (own bin, other bin).  N6 (unbinned.py:111-186): nothing is
+  // excluded, the tallies go per (scaffold of the contig, bin) with a 7th counter (closest in TD and in coverage space)
+  const int32_t* group;          // [U] tally row of the query, or nullptr
+  const int32_t* exclude;        // [U] core skipped by the query, or nullptr
+  int32_t* table;                // [n_groups][B][table_stride] or nullptr
+  int64_t n_groups;
+  int table_stride;              // 6 or 7
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -47,7 +51,8 @@ __global__ void __launch_bounds__(256) refine_kernel(const RefineParams P) {
   const double ugc = I.u_gc[u], ucov = I.u_cov[u], tdb = I.u_td_bound[u];
   const int gcl = I.u_gc_lbin[u], covl = I.u_cov_lbin[u];
   const double cov_lo = I.cov_lo[covl], cov_hi = I.cov_hi[covl];
-  const int64_t own = P.own ? P.own[u] : -1;
+  const int64_t own = P.exclude ? P.exclude[u] : -1;
+  const int64_t grp = P.group ? P.group[u] : 0;
   const bool all_td = P.out.within || P.table;           // the TD flag of every core is wanted
   int best[3] = {-1, -1, -1};
   double bestd[3] = {1e9, 1e9, 1e9};                     // refineBins.py:56
@@ -98,8 +103,8 @@ __global__ void __launch_bounds__(256) refine_kernel(const RefineParams P) {
     }
     if (P.out.within && c < B)
       P.out.within[u * B + c] = (uint8_t)((p_gc ? 1 : 0) | (p_cov ? 2 : 0) | ((m_td >> lane & 1u) ? 4 : 0));
-    if (P.table && c < B && c != own) {                  // merge.py:112-119, bin2 != bin1
-      int32_t* t = P.table + (own * B + c) * 6;
+    if (P.table && c < B && c != own) {                  // merge.py:112-119 (bin2 != bin1), unbinned.py:137-152
+      int32_t* t = P.table + (grp * B + c) * P.table_stride;
       if (p_gc) atomicAdd(t, 1);
       if (p_cov) atomicAdd(t + 1, 1);
       if (m_td >> lane & 1u) atomicAdd(t + 2, 1);
@@ -109,10 +114,11 @@ __global__ void __launch_bounds__(256) refine_kernel(const RefineParams P) {
     if (P.out.closest) { P.out.closest[u * 3] = best[0]; P.out.closest[u * 3 + 1] = best[1]; P.out.closest[u * 3 + 2] = best[2]; }
     if (P.out.min_dist) { P.out.min_dist[u * 3] = bestd[0]; P.out.min_dist[u * 3 + 1] = bestd[1]; P.out.min_dist[u * 3 + 2] = bestd[2]; }
     if (P.out.assigned) P.out.assigned[u] = (best[0] >= 0 && best[0] == best[1] && best[0] == best[2]) ? best[0] : -1;
-    if (P.table) {                                       // merge.py:147-152
+    if (P.table) {                                       // merge.py:147-152, unbinned.py:174-182
       #pragma unroll
       for (int i = 0; i < 3; ++i)
-        if (best[i] >= 0) atomicAdd(P.table + (own * B + best[i]) * 6 + 3 + i, 1);
+        if (best[i] >= 0) atomicAdd(P.table + (grp * B + best[i]) * P.table_stride + 3 + i, 1);
+      if (P.table_stride == 7 && best[1] >= 0 && best[1] == best[2]) atomicAdd(P.table + (grp * B + best[1]) * 7 + 6, 1);
     }
   }
 }
@@ -142,24 +148,34 @@ int check_input(const dbb_refine_input* in, const dbb_refine_output* out) {
   return DBB_OK;
 }
 
-int launch(const dbb_refine_input* in, const dbb_refine_output* out, const int32_t* d_own, int32_t* d_table, cudaStream_t st) {
+struct Tally {                    // device pointers (launch) or host pointers (run_host)
+  const int32_t* group = nullptr; const int32_t* exclude = nullptr; int32_t* table = nullptr;
+  int64_t n_groups = 0; int stride = 6;
+  size_t table_bytes(int64_t B) const { return (size_t)n_groups * (size_t)B * stride * sizeof(int32_t); }
+};
+
+int launch(const dbb_refine_input* in, const dbb_refine_output* out, const Tally& tl, cudaStream_t st) {
   RefineParams P;
-  P.in = *in; P.out = *out; P.own = d_own; P.table = d_table;
+  P.in = *in; P.out = *out; P.group = tl.group; P.exclude = tl.exclude; P.table = tl.table; P.n_groups = tl.n_groups;
+  P.table_stride = tl.stride;
+  int32_t* d_table = tl.table;
   const int64_t grid = (in->n_unbinned + 7) / 8;
   DBB_REQUIRE(grid < (1ll << 31), "too many query contigs for one launch");
-  if (d_table) DBB_CUDA_TRY(cudaMemsetAsync(d_table, 0, (size_t)in->n_cores * in->n_cores * 6 * sizeof(int32_t), st));
+  if (d_table && tl.table_bytes(in->n_cores)) DBB_CUDA_TRY(cudaMemsetAsync(d_table, 0, tl.table_bytes(in->n_cores), st));
   refine_kernel<<<(unsigned)grid, 256, 0, st>>>(P);
   DBB_CUDA_TRY(cudaGetLastError());
   return DBB_OK;
 }
 
-// host buffers in / out: uploads, one launch, downloads (own / table: the N5 variant, both or neither)
-int run_host(const dbb_refine_input* in, const dbb_refine_output* out, const int32_t* own, int32_t* table) {
+// host buffers in / out: uploads, one launch, downloads (tl: the tallies of N5 / N6, host pointers)
+int run_host(const dbb_refine_input* in, const dbb_refine_output* out, const Tally& tl) {
+  int32_t* table = tl.table;
   const size_t U = (size_t)in->n_unbinned, B = (size_t)in->n_cores;
   int rc = DBB_OK;
   cudaStream_t st;
   DBB_CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-  Buf usig, csig, ugc, ucov, cgc, ccov, utd, ugl, ucl, cgm, glo, ghi, clo, chi, o_cl, o_md, o_as, o_wi, b_own, o_tb;
+  Buf usig, csig, ugc, ucov, cgc, ccov, utd, ugl, ucl, cgm, glo, ghi, clo, chi, o_cl, o_md, o_as, o_wi, b_grp, b_exc, o_tb;
+  Tally dtl = tl;
   dbb_refine_input d = *in;
   dbb_refine_output o = *out;
   do {
@@ -169,19 +185,20 @@ int run_host(const dbb_refine_input* in, const dbb_refine_output* out, const int
     UP(glo, gc_lo, (size_t)in->gc_nm * in->gc_nl) UP(ghi, gc_hi, (size_t)in->gc_nm * in->gc_nl)
     UP(clo, cov_lo, (size_t)in->cov_nl) UP(chi, cov_hi, (size_t)in->cov_nl)
 #undef UP
-    if (own && (rc = b_own.up(own, U, st)) != DBB_OK) break;
-    if (table && (rc = o_tb.alloc(B * B * 6 * sizeof(int32_t))) != DBB_OK) break;
+    if (tl.group) { if ((rc = b_grp.up(tl.group, U, st)) != DBB_OK) break; dtl.group = (const int32_t*)b_grp.p; }
+    if (tl.exclude) { if ((rc = b_exc.up(tl.exclude, U, st)) != DBB_OK) break; dtl.exclude = (const int32_t*)b_exc.p; }
+    if (table) { if ((rc = o_tb.alloc(tl.table_bytes(B))) != DBB_OK) break; dtl.table = (int32_t*)o_tb.p; }
     if (out->closest) { if ((rc = o_cl.alloc(U * 12)) != DBB_OK) break; o.closest = (int32_t*)o_cl.p; }
     if (out->min_dist) { if ((rc = o_md.alloc(U * 24)) != DBB_OK) break; o.min_dist = (double*)o_md.p; }
     if (out->assigned) { if ((rc = o_as.alloc(U * 4)) != DBB_OK) break; o.assigned = (int32_t*)o_as.p; }
     if (out->within) { if ((rc = o_wi.alloc(U * std::max<size_t>(B, 1))) != DBB_OK) break; o.within = (uint8_t*)o_wi.p; }
-    if ((rc = launch(&d, &o, (const int32_t*)b_own.p, (int32_t*)o_tb.p, st)) != DBB_OK) break;
+    if ((rc = launch(&d, &o, dtl, st)) != DBB_OK) break;
     cudaError_t e = cudaSuccess;
     if (out->closest) e = cudaMemcpyAsync(out->closest, o.closest, U * 12, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess && out->min_dist) e = cudaMemcpyAsync(out->min_dist, o.min_dist, U * 24, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess && out->assigned) e = cudaMemcpyAsync(out->assigned, o.assigned, U * 4, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess && out->within && B) e = cudaMemcpyAsync(out->within, o.within, U * B, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess && table && B) e = cudaMemcpyAsync(table, o_tb.p, B * B * 6 * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && table && tl.table_bytes(B)) e = cudaMemcpyAsync(table, o_tb.p, tl.table_bytes(B), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) { dbb::set_error("filtered nearest-core search failed: %s", cudaGetErrorString(e)); rc = DBB_ERR_CUDA; }
   } while (0);
@@ -202,13 +219,13 @@ int check_merge(const dbb_merge_input* in, const int32_t* table) {
 DBB_EXPORT int dbb_refine_dev(const dbb_refine_input* in, const dbb_refine_output* out, void* stream) {
   int rc = check_input(in, out);
   if (rc != DBB_OK || in->n_unbinned == 0) return rc;
-  return launch(in, out, nullptr, nullptr, (cudaStream_t)stream);
+  return launch(in, out, Tally(), (cudaStream_t)stream);
 }
 
 DBB_EXPORT int dbb_refine_host(const dbb_refine_input* in, const dbb_refine_output* out) {
   int rc = check_input(in, out);
   if (rc != DBB_OK || in->n_unbinned == 0) return rc;
-  return run_host(in, out, nullptr, nullptr);
+  return run_host(in, out, Tally());
 }
 
 // N5: merge.py:96-156.  own[] values are the caller's responsibility on the device entry point; the host entry
@@ -224,7 +241,9 @@ DBB_EXPORT int dbb_merge_table_dev(const dbb_merge_input* in, int32_t* d_table, 
     DBB_CUDA_TRY(cudaMemsetAsync(d_table, 0, (size_t)in->search.n_cores * in->search.n_cores * 6 * sizeof(int32_t), (cudaStream_t)stream));
     return DBB_OK;
   }
-  return launch(&in->search, &out, in->own, d_table, (cudaStream_t)stream);
+  Tally tl;
+  tl.group = in->own; tl.exclude = in->own; tl.table = d_table; tl.n_groups = in->search.n_cores; tl.stride = 6;
+  return launch(&in->search, &out, tl, (cudaStream_t)stream);
 }
 
 DBB_EXPORT int dbb_merge_table_host(const dbb_merge_input* in, int32_t* table, int32_t* closest) {
@@ -238,5 +257,49 @@ DBB_EXPORT int dbb_merge_table_host(const dbb_merge_input* in, int32_t* table, i
   memset(table, 0, (size_t)B * B * 6 * sizeof(int32_t));
   if (U == 0) return DBB_OK;
   for (int64_t u = 0; u < U; ++u) DBB_REQUIRE(in->own[u] >= 0 && in->own[u] < B, "own[] out of range");
-  return run_host(&in->search, &out, in->own, table);
+  Tally tl;
+  tl.group = in->own; tl.exclude = in->own; tl.table = table; tl.n_groups = B; tl.stride = 6;
+  return run_host(&in->search, &out, tl);
+}
+
+// N6: unbinned.py:111-186.  The scaffold's contigs against every bin; nothing excluded; 7 counters per (scaffold, bin).
+namespace {
+int check_unbinned(const dbb_unbinned_input* in, const int32_t* table) {
+  DBB_REQUIRE(in && table, "NULL argument");
+  DBB_REQUIRE(in->n_groups >= 0 && (in->search.n_unbinned == 0 || in->group), "the scaffold index of every contig is required");
+  DBB_REQUIRE((double)in->n_groups * (double)in->search.n_cores * 7.0 < 2147483648.0, "table too large");
+  return DBB_OK;
+}
+}  // namespace
+
+DBB_EXPORT int dbb_unbinned_table_dev(const dbb_unbinned_input* in, int32_t* d_table, void* stream) {
+  int rc = check_unbinned(in, d_table);
+  if (rc != DBB_OK) return rc;
+  dbb_refine_output out = {nullptr, nullptr, nullptr, nullptr};
+  dbb_refine_output chk = out;
+  chk.assigned = d_table;
+  if ((rc = check_input(&in->search, &chk)) != DBB_OK) return rc;
+  Tally tl;
+  tl.group = in->group; tl.table = d_table; tl.n_groups = in->n_groups; tl.stride = 7;
+  if (in->search.n_unbinned == 0) {
+    if (tl.table_bytes(in->search.n_cores)) DBB_CUDA_TRY(cudaMemsetAsync(d_table, 0, tl.table_bytes(in->search.n_cores), (cudaStream_t)stream));
+    return DBB_OK;
+  }
+  return launch(&in->search, &out, tl, (cudaStream_t)stream);
+}
+
+DBB_EXPORT int dbb_unbinned_table_host(const dbb_unbinned_input* in, int32_t* table) {
+  int rc = check_unbinned(in, table);
+  if (rc != DBB_OK) return rc;
+  dbb_refine_output out = {nullptr, nullptr, nullptr, nullptr};
+  dbb_refine_output chk = out;
+  chk.assigned = table;
+  if ((rc = check_input(&in->search, &chk)) != DBB_OK) return rc;
+  const int64_t U = in->search.n_unbinned, B = in->search.n_cores;
+  Tally tl;
+  tl.group = in->group; tl.table = table; tl.n_groups = in->n_groups; tl.stride = 7;
+  memset(table, 0, tl.table_bytes(B));
+  if (U == 0) return DBB_OK;
+  for (int64_t u = 0; u < U; ++u) DBB_REQUIRE(in->group[u] >= 0 && in->group[u] < in->n_groups, "group[] out of range");
+  return run_host(&in->search, &out, tl);
 }

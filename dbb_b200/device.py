@@ -262,6 +262,20 @@ def pairs_pruned(sig_padded, dt, row0=0, row1=None, k=0, topk_filter=0, want_cou
             order[torch.argsort(dt.td_bound, stable=True)] = torch.arange(n, device=dev)
             cls = ((order * n_classes) // max(n, 1)).to(torch.float32)
             dt._prune_class, dt._prune_nc = cls, n_classes
+    if len(range(rank, (row1 - row0 + T - 1) // T, world)) == 0:
+        # more ranks than row tiles: nothing for this one
+        res = {'row_ids': torch.empty(0, dtype=torch.int64, device=dev), 'tiles_visited': 0, 'tiles_total': 0, 'launches': 0}
+        if k > 0:
+            res['idx'] = torch.empty((0, k), dtype=torch.int32, device=dev)
+            res['dist'] = torch.empty((0, k), dtype=torch.float32, device=dev)
+        if want_count:
+            res['count'] = torch.empty(0, dtype=torch.int32, device=dev)
+            res['neighbour_bp'] = torch.empty(0, dtype=torch.int64, device=dev)
+        if isinstance(timings, list):
+            for name in ('plan', 'sweep', 'second sweep + merge'):
+                mark(name)
+            timings.append(marks)
+        return res
     b = _prune_buffers(dt, n, row0, row1, world, dev)
     st = b.st
     L = _lib.lib()

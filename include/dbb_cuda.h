@@ -282,6 +282,23 @@ typedef struct {
 int dbb_merge_table_dev(const dbb_merge_input* in, int32_t* d_table, int32_t* d_closest, void* stream);
 int dbb_merge_table_host(const dbb_merge_input* in_host, int32_t* table, int32_t* closest);
 
+/* ---- N6: statistics of unbinned scaffolds -- Unbinned.run, unbinned.py:111-186 ----------------------------------
+ * The same search once more: queries = the contigs of the scaffolds under study, group[u] = index of the contig's
+ * scaffold, cores = the bins (array order = the order unbinned.py iterates `bins`), nothing excluded.  Per
+ * (scaffold s, bin b), over the contigs of s:
+ *   table[s][b][0..2] = within the GC / coverage / TD distribution of b (:137-152),
+ *   table[s][b][3..5] = b is the closest valid bin in GC / TD / coverage space (:156-178; the search only runs for
+ *                       contigs within all three of b, which "b is the closest VALID bin" implies),
+ *   table[s][b][6]    = b is the closest in TD and in coverage space (the binning score's numerator, :181-182).
+ * table is int32 [n_groups][B][7], zeroed by the call. */
+typedef struct {
+  dbb_refine_input search;
+  const int32_t* group;        /* [U], each in [0, n_groups) */
+  int64_t n_groups;
+} dbb_unbinned_input;
+int dbb_unbinned_table_dev(const dbb_unbinned_input* in, int32_t* d_table, void* stream);
+int dbb_unbinned_table_host(const dbb_unbinned_input* in_host, int32_t* table);
+
 /* dense [n][136] -> padded [n][DBB_SIG_STRIDE] on device (used after the all-gather) */
 int dbb_pad_signatures_dev(const float* d_dense, int64_t n, float* d_padded, void* stream);
 

@@ -575,6 +575,98 @@ def merge_table_literal(contigs, distributions, numKmers=NUM_KMERS):
 
 
 # ----------------------------------------------------------------------------------------------
+# N6: statistics of unbinned scaffolds -- unbinned.py:70-186
+# ----------------------------------------------------------------------------------------------
+
+UNBINNED_HEADER = ('Scaffold Id\tLength\tGC\tCoverage\tBin Id\tGC\tCoverage\tContigs in Scaffold\tWithin GC\tWithin coverage\t'
+                   'Within tetra\tClosest GC\tClosest coverage\tClosest tetra\tBinning score\n')       # unbinned.py:110
+
+
+def unbinned_table_literal(contigs, distributions, minScaffoldLen, minContigLen, allScaffolds, numKmers=NUM_KMERS):
+    """unbinned.py:70-186 for ``contigs`` in the order unbinned.py meets them (contigId, length, GC, coverage, tetraSig,
+    binId; -1 = unbinned).  Scaffolds and bins are visited in order of first appearance.  Returns the text it writes."""
+    import re
+    bins = {}
+    unbinnedContigs = {}
+    for contig in contigs:
+        scaffoldId = contig.contigId
+        match = re.search('_c[0-9]*$', contig.contigId)
+        if match:
+            scaffoldId = contig.contigId[0:match.start()]
+        if contig.length < minContigLen:
+            continue
+        if contig.binId == -1:
+            unbinnedContigs.setdefault(scaffoldId, []).append(contig)
+        else:
+            if contig.binId not in bins:
+                bins[contig.binId] = Core(contig.binId, 0, 0, 0, [0] * numKmers)
+            b = bins[contig.binId]
+            b.length += contig.length
+            weight = float(contig.length) / b.length
+            b.GC = contig.GC * weight + b.GC * (1.0 - weight)
+            b.coverage = contig.coverage * weight + b.coverage * (1.0 - weight)
+            for i in range(0, len(b.tetraSig)):
+                b.tetraSig[i] = contig.tetraSig[i] * weight + b.tetraSig[i] * (1.0 - weight)
+            if allScaffolds:
+                unbinnedContigs.setdefault(scaffoldId, []).append(contig)
+    sig_of = dict((k, np.asarray(v.tetraSig, dtype=np.float64)) for k, v in bins.items())
+    out = [UNBINNED_HEADER]
+    for scaffoldId, cs in unbinnedContigs.items():
+        for queryBinId, queryBin in bins.items():
+            numWithinGC = numWithinCov = numWithinTetra = closestGC = closestCov = closestTetra = binningScore = 0
+            scaffoldGC = scaffoldCov = scaffoldLen = 0
+            for contig in cs:
+                scaffoldLen += contig.length
+                weight = float(contig.length) / scaffoldLen
+                scaffoldGC = contig.GC * weight + scaffoldGC * (1.0 - weight)
+                scaffoldCov = contig.coverage * weight + scaffoldCov * (1.0 - weight)
+                tdDistanceQuery = distance(contig.tetraSig, sig_of[queryBinId])
+                bInDists = True
+                if distributions.withinDistGC(contig, queryBin):
+                    numWithinGC += 1
+                else:
+                    bInDists = False
+                if distributions.withinDistCov(contig, queryBin):
+                    numWithinCov += 1
+                else:
+                    bInDists = False
+                if distributions.witinDistTD(tdDistanceQuery, contig):
+                    numWithinTetra += 1
+                else:
+                    bInDists = False
+                closestBin = [None] * 3
+                minDistances = [1e9] * 3
+                if bInDists:
+                    for binId, b in bins.items():
+                        if not distributions.withinDistGC(contig, b):
+                            continue
+                        if not distributions.withinDistCov(contig, b):
+                            continue
+                        tdDistance = distance(contig.tetraSig, sig_of[binId])
+                        if not distributions.witinDistTD(tdDistance, contig):
+                            continue
+                        distances = [abs(contig.GC - b.GC), tdDistance, abs(contig.coverage - b.coverage)]
+                        for i, d in enumerate(distances):
+                            if d < minDistances[i]:
+                                minDistances[i] = d
+                                closestBin[i] = binId
+                if closestBin[0] == queryBinId:
+                    closestGC += 1
+                if closestBin[1] == queryBinId:
+                    closestCov += 1
+                if closestBin[2] == queryBinId:
+                    closestTetra += 1
+                if closestBin[1] == queryBinId and closestBin[2] == queryBinId:
+                    binningScore += 1
+            if scaffoldLen >= minScaffoldLen:
+                out.append('%s\t%d\t%.1f\t%.1f\t%s\t%.1f\t%.1f\t%d' % (scaffoldId, scaffoldLen, scaffoldGC * 100, scaffoldCov, queryBinId,
+                                                                       queryBin.GC * 100, queryBin.coverage, len(cs)))
+                out.append('\t%d\t%d\t%d\t%d\t%d\t%d' % (numWithinGC, numWithinCov, numWithinTetra, closestGC, closestCov, closestTetra))
+                out.append('\t%.2f\n' % (float(binningScore) / len(cs)))
+    return ''.join(out)
+
+
+# ----------------------------------------------------------------------------------------------
 # N2: sequence side of preprocess -- splitScaffolds.py:27-53, seqUtils.py:258-265,
 # preprocess.py:94-100, :118-161 (what a worker computes from the sequence alone)
 # ----------------------------------------------------------------------------------------------

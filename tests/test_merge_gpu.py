@@ -1,5 +1,5 @@
-"""N5 row: the bin-to-bin merge table (merge.py) against the reference's own output files (golden) and the oracle's
-literal loop."""
+"""N5 / N6 rows: the bin-to-bin merge table (merge.py) and the statistics of unbinned scaffolds (unbinned.py) against the
+reference's own output files (golden) and the oracle's literal loops."""
 import ast
 import os
 
@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from oracle import dbb_oracle as O
-from tests.test_oracle_golden import merge_case
+from tests.test_oracle_golden import merge_case, unbinned_case
 
 pytestmark = pytest.mark.gpu
 
@@ -113,3 +113,56 @@ def test_merge_table_degenerate_inputs():
     bins, table = Merge().mergeTable([c], gcDist, 99, td, 99, covDist, 99)
     assert len(bins) == 1 and table.tolist() == [[[0] * 6]]
     assert Merge().formatTable(bins, table) == O.MERGE_HEADER
+
+
+def test_unbinned_run_writes_the_reference_file(tmp_path):
+    """Unbinned.run through real files (unbinned.py:38) == the file the reference's own Unbinned.run wrote."""
+    from dbb_b200.unbinned import Unbinned
+    for tag in 'ab':
+        g, contigs, pr, gcDist, td, covDist = unbinned_case(tag)
+        d = str(tmp_path / tag)
+        os.makedirs(d)
+        data = _write_inputs(d, contigs, gcDist, td, covDist)
+        out = os.path.join(d, 'unbinned.tsv')
+        Unbinned().run(d, os.path.join(d, 'bins.tsv'), pr[0], pr[1], pr[2], pr[3], pr[4], bool(pr[5]), out, dataDir=data)
+        assert open(out).read() == str(g[tag + '_unbinned_tsv']), tag
+
+
+def test_unbinned_table_random_instance_vs_literal_loop():
+    """900 contigs in scaffolds of 1-5 contigs, 4 genomes cut into 12 bins, a third unbinned; the whole file against the
+    literal loop, for unbinned scaffolds only and for all scaffolds."""
+    from dbb_b200 import synthetic
+    from dbb_b200.data import load_td_dist
+    from dbb_b200.genomicSignatures import GenomicSignatures
+    from dbb_b200.unbinned import Unbinned
+    n = 900
+    meta = synthetic.make_metagenome(seed=71, n_scaffolds=n, min_len=1000, max_len=25000, n_genomes=4)
+    seqs = synthetic.generate_sequences(meta)
+    counts, _ = GenomicSignatures(4, 1).signatures(seqs, want_freq=False)
+    sig = counts.astype(np.float64) / counts.sum(axis=1, keepdims=True)
+    rng = np.random.RandomState(71)
+    order = np.argsort(meta.genome, kind='stable')
+    contigs, pos, sc = [None] * n, 0, 0
+    while pos < n:
+        members = order[pos:pos + int(rng.randint(1, 6))]
+        unb = rng.rand() < 0.33
+        for k, i in enumerate(members):
+            c = O.Contig('s%d_c%d' % (sc, k) if len(members) > 1 else 's%d' % sc, int(meta.length[i]), float(meta.gc_obs[i]),
+                         float(meta.coverage[i]), sig[i])
+            c.binId = -1 if unb else 'bin%d' % (int(meta.genome[i]) * 3 + int(rng.randint(0, 3)))
+            contigs[i] = c
+        pos += len(members)
+        sc += 1
+    td = load_td_dist()
+    gcDist, covDist = synthetic.synthetic_gc_dist(sorted(td.keys())), synthetic.synthetic_cov_dist(seed=7)
+    dist = O.Distributions(gcDist, 95, td, 99, covDist, 99)
+    import tempfile
+    for allScaffolds, minS, minC in ((False, 5000, 1500), (True, 0, 0)):
+        with tempfile.TemporaryDirectory() as d:
+            data = _write_inputs(d, contigs, gcDist, td, covDist)
+            out = os.path.join(d, 'u.tsv')
+            Unbinned().run(d, os.path.join(d, 'bins.tsv'), 95, 99, 99, minS, minC, allScaffolds, out, dataDir=data)
+            got = open(out).read()
+        want = O.unbinned_table_literal(contigs, dist, minS, minC, allScaffolds)
+        assert got == want, allScaffolds
+        assert len(want.split('\n')) > 500

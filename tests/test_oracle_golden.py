@@ -221,3 +221,30 @@ def test_merge_oracle_matches_reference_outputs():
         assert O.merge_table_literal(contigs, dist) == str(g[tag + '_merge_tsv']), tag
     rows = [r.split('\t') for r in str(g['c_merge_tsv']).strip().split('\n')[1:]]
     assert any(r[10] != r[11] or r[11] != r[12] for r in rows)
+
+
+def unbinned_case(tag):
+    """(golden, contigs in file order with binId set, [gcPer, tdPer, covPer, minScaffoldLen, minContigLen, allScaffolds],
+    gcDist, tdDist, covDist) of the N6 golden vectors (tests/golden/make_golden_unbinned.py)."""
+    from dbb_b200 import synthetic
+    from dbb_b200.data import load_td_dist
+    g = util.golden_npz('ref_unbinned.npz')
+    td = load_td_dist()
+    gcDist, covDist = synthetic.synthetic_gc_dist(sorted(td.keys())), synthetic.synthetic_cov_dist(seed=7)
+    contigs = []
+    for i in range(len(g[tag + '_length'])):
+        c = O.Contig(str(g[tag + '_id'][i]), int(g[tag + '_length'][i]), float(g[tag + '_gc'][i]), float(g[tag + '_cov'][i]),
+                     g[tag + '_sig'][i])
+        b = str(g[tag + '_bin'][i])
+        c.binId = -1 if b == 'unbinned' else b
+        contigs.append(c)
+    return g, contigs, [int(x) for x in g[tag + '_params']], gcDist, td, covDist
+
+
+def test_unbinned_oracle_matches_reference_outputs():
+    """N6 row: the literal restatement of unbinned.py:70-186 writes, byte for byte, the file the reference's own
+    Unbinned.run wrote (case a: length thresholds, unbinned scaffolds only; case b: all scaffolds)."""
+    for tag in 'ab':
+        g, contigs, pr, gcDist, td, covDist = unbinned_case(tag)
+        dist = O.Distributions(gcDist, pr[0], td, pr[1], covDist, pr[2])
+        assert O.unbinned_table_literal(contigs, dist, pr[3], pr[4], bool(pr[5])) == str(g[tag + '_unbinned_tsv']), tag

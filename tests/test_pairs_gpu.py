@@ -326,6 +326,40 @@ def test_pruned_sweep_equals_full_sweep():
             assert torch.equal(part[key], full[key][ids]), (key, r0)
 
 
+def test_pruned_sweep_with_nan_signatures_and_ranks_beyond_the_row_tiles():
+    """Scaffolds without a valid window have NaN signatures (genomicSignatures.py:147-148): the planner leaves them out of
+    the tile intervals, and a whole row tile of them still writes its (empty) results.  Also more ranks than row tiles."""
+    import torch
+    from dbb_b200 import device, synthetic
+    from dbb_b200.distributions import PairTables
+    from dbb_b200.genomicSignatures import GenomicSignatures
+    meta = synthetic.make_metagenome(seed=52, n_scaffolds=900, min_len=1000, max_len=30000, n_genomes=5)
+    seqs = synthetic.generate_sequences(meta)
+    _, freq = GenomicSignatures(4, 1).signatures(seqs)
+    freq[7] = np.nan
+    freq[300:450] = np.nan                                              # more than one whole tile of the sorted order
+    sig = device.pad_signatures(torch.from_numpy(freq).cuda())
+    td, _, _ = _dists()
+    n = meta.n_scaffolds
+    for filt, ncls in ((0, 1), (device.FILTER_TD, 8)):                   # one class: the 151 NaN rows fill the first tile
+        dt = device.DevicePairTables(PairTables(meta.length, tdDist=td, tdDistPer=80))
+        full = device.pairs(sig, dt, k=20, topk_filter=filt, want_count=True)
+        got = device.unsort_rows(device.pairs_pruned(sig, dt, k=20, topk_filter=filt, want_count=True, n_classes=ncls), n)
+        for key in ('idx', 'dist', 'count', 'neighbour_bp'):
+            assert torch.equal(got[key], full[key]), (key, filt)
+        assert int(full['count'][7]) == 0 and int(full['idx'][7, 0]) == -1
+    dt = device.DevicePairTables(PairTables(meta.length, tdDist=td, tdDistPer=80))
+    full = device.pairs(sig, dt, k=20, want_count=True)
+    seen = 0
+    for rank in range(10):                                              # 8 row tiles, 10 ranks: ranks 8 and 9 get nothing
+        part = device.pairs_pruned(sig, dt, k=20, want_count=True, part=(rank, 10))
+        ids = part['row_ids']
+        seen += int(ids.numel())
+        for key in ('idx', 'dist', 'count', 'neighbour_bp'):
+            assert torch.equal(part[key], full[key][ids]), (key, rank)
+    assert seen == n
+
+
 def test_tdneighbours_knn_public_api_pruned_and_plain_agree_with_the_oracle():
     """TdNeighbours.knn (the array-native addition of SURVEY 8b): the default (pruned sweep) and prune=False (plain sweep
     through dbb_pairs_host) return the same arrays, and those match the oracle's k-NN and TD neighbourhood sizes."""
