@@ -518,7 +518,7 @@ def run_ours(args):
                            'note': 'achieved / frac: lane-ops of the pairs actually computed over the time of the sweep launches; frac_resolved: '
                                    '272 lane-ops for every pair of the N x N problem over the whole stage (planning included), i.e. what a full sweep '
                                    'would have to sustain to be as fast',
-                           'traffic': traffic.get('pairs_dram_bytes_per_step') if args.workload == 'C2' and args.scale == 1.0 and world == 1 and args.no_prune else None,
+                           'traffic': traffic.get('pairs_dram_bytes_per_step' if args.no_prune else 'pairs_pruned_dram_bytes_per_launch') if args.workload == 'C2' and args.scale == 1.0 and world == 1 else None,
                            'peak_source': '%d SMs x 128 FP32 lanes x %.0f MHz (272 lane-ops per pair)' % (sm_count, sm_max_mhz)},
         'e2e': None if args.no_e2e else {'value': total_bp / e2e_count_s / 1e9, 'unit': 'Gbp/s', 'value2': pairs_total / max(e2e_s - e2e_count_s, 1e-9),
                 'unit2': 'scaffold-pairs/s', 'ms_per_step': e2e_s * 1e3, 'steps': e2e_steps,
