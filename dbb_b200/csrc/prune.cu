@@ -205,7 +205,7 @@ __device__ __forceinline__ bool visit(const Stats& S, int rt, int ct, float pmin
   return S.second ? (!empty && lb <= thr && !first) : first;
 }
 
-__global__ void __launch_bounds__(256) count_kernel(Stats S, const uint8_t* __restrict__ mine, int32_t* __restrict__ cnt) {
+__global__ void __launch_bounds__(256) tile_count_kernel(Stats S, const uint8_t* __restrict__ mine, int32_t* __restrict__ cnt) {
   __shared__ int s_cnt[8];
   const int rt = blockIdx.x, t = threadIdx.x;
   int c = 0;
@@ -356,7 +356,7 @@ int build_lists(const dbb_prune_input* in, const dbb_prune_buffers* buf, const L
   int32_t *oval_in = (int32_t*)(sc + L.oval_in), *oval_out = (int32_t*)(sc + L.oval_out);
   const unsigned n_rt = (unsigned)L.n_rt, g256 = (n_rt + 255) / 256;
   size_t cub_bytes = L.cub_bytes;
-  count_kernel<<<n_rt, 256, 0, st>>>(S, second ? buf->mine : nullptr, cnt);
+  tile_count_kernel<<<n_rt, 256, 0, st>>>(S, second ? buf->mine : nullptr, cnt);
   if (!second) {
     if (in->world > 1) {
       order_keys_kernel<<<g256, 256, 0, st>>>(cnt, L.n_rt, okey_in, oval_in);
