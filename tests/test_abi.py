@@ -74,6 +74,36 @@ def test_no_cpu_fallback_without_a_gpu():
     from dbb_b200.distributions import PairTables
     with pytest.raises(_lib.DbbError):
         _pairs.run_pairs_host(np.zeros((4, 136), np.float32), PairTables(np.array([1000, 2000, 3000, 4000])), k=2)
+    # the callers around the path (N1, N3, N5, N6): same rule
+    from dbb_b200 import synthetic
+    from dbb_b200.data import load_td_dist
+    from dbb_b200.merge import Contig, Merge
+    from dbb_b200.unbinned import Scaffold, Unbinned
+    from dbb_b200.refineBins import RefineBins, coreStatistics
+    from dbb_b200.greedy import Greedy
+    td = load_td_dist()
+    gcDist, covDist = synthetic.synthetic_gc_dist(sorted(td.keys())), synthetic.synthetic_cov_dist(seed=7)
+    cs = []
+    for i in range(4):
+        c = Contig('c%d' % i, 5000 + i, 0.5, 10.0, np.full(136, 1 / 136.0))
+        c.binId = 'b%d' % (i % 2)
+        cs.append(c)
+    args = (gcDist, 99, td, 99, covDist, 99)
+    with pytest.raises(_lib.DbbError):
+        Merge().mergeTable(cs, *args)
+    sc = Scaffold('s')
+    sc.add(cs[0])
+    with pytest.raises(_lib.DbbError):
+        Unbinned().unbinnedTable([sc], cs[1:], *args)
+    with pytest.raises(_lib.DbbError):
+        RefineBins().closestCores(cs[:1], coreStatistics(cs[1:]), *args)
+    with pytest.raises(_lib.DbbError):
+        Greedy().greedy(cs, 1000, 99, gcDist, td, covDist)
+    # host-side argument checks of the C ABI answer before any CUDA call
+    L = _lib.lib()
+    assert L.dbb_merge_table_host(None, None, None) != 0 and b'NULL' in L.dbb_last_error()
+    assert L.dbb_unbinned_table_host(None, None) != 0
+    assert L.dbb_prune_plan_dev(None, None, None) != 0 and L.dbb_prune_merge_dev(None, 0, 0, None, None, None, None, None) != 0
 
 
 def test_product_never_imports_the_oracle():
