@@ -241,8 +241,8 @@ def run_reference(args):
     line = {'impl': 'reference', 'metric': METRIC, 'value': gbp, 'unit': 'Gbp/s', 'value2': pairs, 'unit2': 'scaffold-pairs/s',
             'n_gpus': args.gpus, 'steps': len(vals), 'warmup': min(args.warmup, 1),
             'ms_per_step': 1e3 * float(np.mean([v['t_count_s'] + v['t_rows_s'] for v in vals])),
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': workload_config(args, 1),
+            'higher_is_better': True, 'scaling': 'weak' if args.workload == 'C2' else 'strong', 'vs_baseline': None, 'dtype': 'f64',
+            'data': 'synthetic', 'config': workload_config(args, max(int(args.gpus), 1)),       # the GPU arm's config at this N
             'cpu_baseline': {'value': gbp, 'unit': 'Gbp/s', 'value2': pairs, 'unit2': 'scaffold-pairs/s', 'cores': cores,
                              'kind': 'port', 'sample': sample},
             'e2e': {'value': gbp, 'unit': 'Gbp/s', 'value2': pairs, 'unit2': 'scaffold-pairs/s',
