@@ -261,13 +261,13 @@ def workload_config(args, world):
                             'neighbourhood (per=%d)' % (args.workload, int((1000000 if args.workload == 'C4' else 250000) * args.scale), world, K_NN,
                                                         'TD+GC+coverage' if args.workload == 'C3' else 'TD', TD_PER),
                 'k': K_NN, 'td_percentile': TD_PER, 'scale': args.scale,
-                'l2_policy': 'inputs larger than L2', 'parallelism': 'scaffolds LPT-sharded for counting, 1 all-gather (NCCL), row-block kNN'}
+                'l2_policy': 'inputs larger than L2', 'parallelism': 'scaffolds LPT-sharded for counting, 1 all-gather (NCCL), kNN row tiles dealt to the ranks by work (equal row blocks with --no-prune)'}
     return {'workload': 'C2 per GPU: %d scaffolds x %d GPU(s), 1-100 kb log-uniform (~1.07 Gbp per GPU), tetramer signatures + '
                         'k=%d TD kNN + TD neighbourhood (per=%d) over all %d scaffolds'
                         % (int(50000 * args.scale), world, K_NN, TD_PER, int(50000 * args.scale) * world),
             'k': K_NN, 'td_percentile': TD_PER, 'scale': args.scale,
             'l2_policy': 'inputs larger than L2 (packed sequence ~400 MB per GPU re-read every step; stage 2 is FP32-bound)',
-            'parallelism': 'scaffolds LPT-sharded for counting, 1 all-gather (NCCL), row-block kNN' if world > 1 else 'single GPU'}
+            'parallelism': 'scaffolds LPT-sharded for counting, 1 all-gather (NCCL), kNN row tiles dealt to the ranks by work (equal row blocks with --no-prune)' if world > 1 else 'single GPU'}
 
 
 def run_ours(args):
