@@ -75,7 +75,7 @@ class UnbinnedInput(ctypes.Structure):
 
 
 class RefineOutput(ctypes.Structure):
-    _fields_ = [('closest', c_vp), ('min_dist', c_vp), ('assigned', c_vp), ('within', c_vp)]
+    _fields_ = [('closest', c_vp), ('min_dist', c_vp), ('assigned', c_vp), ('within', c_vp), ('dist', c_vp)]
 
 
 # name -> (restype, argtypes); this table is also what tests/test_abi.py checks against the header

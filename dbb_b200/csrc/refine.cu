@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(256) refine_kernel(const RefineParams P) {
   const double cov_lo = I.cov_lo[covl], cov_hi = I.cov_hi[covl];
   const int64_t own = P.exclude ? P.exclude[u] : -1;
   const int64_t grp = P.group ? P.group[u] : 0;
-  const bool all_td = P.out.within || P.table;           // the TD flag of every core is wanted
+  const bool all_td = P.out.within || P.out.dist || P.table;   // the TD distance to every core is wanted
   int best[3] = {-1, -1, -1};
   double bestd[3] = {1e9, 1e9, 1e9};                     // refineBins.py:56
 
@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(256) refine_kernel(const RefineParams P) {
         if (k < DBB_NUM_KMERS) part += fabs(us[q] - cs[k]);
       }
       const double d = warp_sum(part);
+      if (P.out.dist && lane == 0) P.out.dist[u * B + c0 + j] = d;
       const bool p_td = d < tdb;                         // distributions.py:103-104 (strict)
       if (p_td) m_td |= 1u << j;
       if (p_td && ((m_gc & m_cov) >> j & 1u) && c0 + j != own) {
@@ -144,7 +145,7 @@ int check_input(const dbb_refine_input* in, const dbb_refine_output* out) {
   DBB_REQUIRE(in->u_sig && in->u_gc && in->u_cov && in->u_td_bound && in->u_gc_lbin && in->u_cov_lbin, "incomplete unbinned inputs");
   DBB_REQUIRE(in->n_cores == 0 || (in->c_sig && in->c_gc && in->c_cov && in->c_gc_mbin), "incomplete core inputs");
   DBB_REQUIRE(in->gc_lo && in->gc_hi && in->cov_lo && in->cov_hi && in->gc_nm > 0 && in->gc_nl > 0 && in->cov_nl > 0, "incomplete tables");
-  DBB_REQUIRE(out->closest || out->assigned || out->within || out->min_dist, "no output requested");
+  DBB_REQUIRE(out->closest || out->assigned || out->within || out->min_dist || out->dist, "no output requested");
   return DBB_OK;
 }
 
@@ -174,7 +175,7 @@ int run_host(const dbb_refine_input* in, const dbb_refine_output* out, const Tal
   int rc = DBB_OK;
   cudaStream_t st;
   DBB_CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-  Buf usig, csig, ugc, ucov, cgc, ccov, utd, ugl, ucl, cgm, glo, ghi, clo, chi, o_cl, o_md, o_as, o_wi, b_grp, b_exc, o_tb;
+  Buf usig, csig, ugc, ucov, cgc, ccov, utd, ugl, ucl, cgm, glo, ghi, clo, chi, o_cl, o_md, o_as, o_wi, o_di, b_grp, b_exc, o_tb;
   Tally dtl = tl;
   dbb_refine_input d = *in;
   dbb_refine_output o = *out;
@@ -192,12 +193,14 @@ int run_host(const dbb_refine_input* in, const dbb_refine_output* out, const Tal
     if (out->min_dist) { if ((rc = o_md.alloc(U * 24)) != DBB_OK) break; o.min_dist = (double*)o_md.p; }
     if (out->assigned) { if ((rc = o_as.alloc(U * 4)) != DBB_OK) break; o.assigned = (int32_t*)o_as.p; }
     if (out->within) { if ((rc = o_wi.alloc(U * std::max<size_t>(B, 1))) != DBB_OK) break; o.within = (uint8_t*)o_wi.p; }
+    if (out->dist) { if ((rc = o_di.alloc(U * std::max<size_t>(B, 1) * 8)) != DBB_OK) break; o.dist = (double*)o_di.p; }
     if ((rc = launch(&d, &o, dtl, st)) != DBB_OK) break;
     cudaError_t e = cudaSuccess;
     if (out->closest) e = cudaMemcpyAsync(out->closest, o.closest, U * 12, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess && out->min_dist) e = cudaMemcpyAsync(out->min_dist, o.min_dist, U * 24, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess && out->assigned) e = cudaMemcpyAsync(out->assigned, o.assigned, U * 4, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess && out->within && B) e = cudaMemcpyAsync(out->within, o.within, U * B, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && out->dist && B) e = cudaMemcpyAsync(out->dist, o.dist, U * B * 8, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess && table && tl.table_bytes(B)) e = cudaMemcpyAsync(table, o_tb.p, tl.table_bytes(B), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) { dbb::set_error("filtered nearest-core search failed: %s", cudaGetErrorString(e)); rc = DBB_ERR_CUDA; }
@@ -233,7 +236,7 @@ DBB_EXPORT int dbb_refine_host(const dbb_refine_input* in, const dbb_refine_outp
 DBB_EXPORT int dbb_merge_table_dev(const dbb_merge_input* in, int32_t* d_table, int32_t* d_closest, void* stream) {
   int rc = check_merge(in, d_table);
   if (rc != DBB_OK) return rc;
-  dbb_refine_output out = {d_closest, nullptr, nullptr, nullptr};
+  dbb_refine_output out = {d_closest, nullptr, nullptr, nullptr, nullptr};
   dbb_refine_output chk = out;
   chk.assigned = reinterpret_cast<int32_t*>(d_table);     // "some output requested" for check_input
   if ((rc = check_input(&in->search, &chk)) != DBB_OK) return rc;
@@ -249,7 +252,7 @@ DBB_EXPORT int dbb_merge_table_dev(const dbb_merge_input* in, int32_t* d_table, 
 DBB_EXPORT int dbb_merge_table_host(const dbb_merge_input* in, int32_t* table, int32_t* closest) {
   int rc = check_merge(in, table);
   if (rc != DBB_OK) return rc;
-  dbb_refine_output out = {closest, nullptr, nullptr, nullptr};
+  dbb_refine_output out = {closest, nullptr, nullptr, nullptr, nullptr};
   dbb_refine_output chk = out;
   chk.assigned = table;
   if ((rc = check_input(&in->search, &chk)) != DBB_OK) return rc;
@@ -275,7 +278,7 @@ int check_unbinned(const dbb_unbinned_input* in, const int32_t* table) {
 DBB_EXPORT int dbb_unbinned_table_dev(const dbb_unbinned_input* in, int32_t* d_table, void* stream) {
   int rc = check_unbinned(in, d_table);
   if (rc != DBB_OK) return rc;
-  dbb_refine_output out = {nullptr, nullptr, nullptr, nullptr};
+  dbb_refine_output out = {nullptr, nullptr, nullptr, nullptr, nullptr};
   dbb_refine_output chk = out;
   chk.assigned = d_table;
   if ((rc = check_input(&in->search, &chk)) != DBB_OK) return rc;
@@ -291,7 +294,7 @@ DBB_EXPORT int dbb_unbinned_table_dev(const dbb_unbinned_input* in, int32_t* d_t
 DBB_EXPORT int dbb_unbinned_table_host(const dbb_unbinned_input* in, int32_t* table) {
   int rc = check_unbinned(in, table);
   if (rc != DBB_OK) return rc;
-  dbb_refine_output out = {nullptr, nullptr, nullptr, nullptr};
+  dbb_refine_output out = {nullptr, nullptr, nullptr, nullptr, nullptr};
   dbb_refine_output chk = out;
   chk.assigned = table;
   if ((rc = check_input(&in->search, &chk)) != DBB_OK) return rc;

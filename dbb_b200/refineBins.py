@@ -76,10 +76,11 @@ class RefineBins(object):
         self.logger = logging.getLogger()
 
     def closestCores(self, unbinnedContigs, cores, gcDist, gcDistPer, tdDist, tdDistPer, covDist, covDistPer,
-                     want_within=False):
+                     want_within=False, want_dist=False):
         """For every unbinned contig: (closest int32[U,3] core POSITION in GC / TD / coverage space or -1,
-        min_dist float64[U,3], assigned int32[U] position or -1[, within uint8[U,B]]).  ``cores`` is a dict
-        binId -> Core (iterated in ascending binId order, which is CPython-2.7's order for small ints) or a list."""
+        min_dist float64[U,3], assigned int32[U] position or -1[, within uint8[U,B]][, dist float64[U,B]]).  ``cores``
+        is a dict binId -> Core (iterated in ascending binId order, which is CPython-2.7's order for small ints) or a
+        list (taken in the given order)."""
         core_list = [cores[k] for k in sorted(cores)] if isinstance(cores, dict) else list(cores)
         U, B = len(unbinnedContigs), len(core_list)
         inp, keep = searchInput(unbinnedContigs, core_list, gcDist, gcDistPer, tdDist, tdDistPer, covDist, covDistPer)
@@ -87,12 +88,17 @@ class RefineBins(object):
         mind = np.full((U, 3), 1e9, dtype=np.float64)
         assigned = np.full(U, -1, dtype=np.int32)
         within = np.zeros((U, max(B, 1)), dtype=np.uint8) if want_within else None
+        dmat = np.zeros((U, max(B, 1)), dtype=np.float64) if want_dist else None
         if U:
-            out = _lib.RefineOutput(_lib.ptr(closest), _lib.ptr(mind), _lib.ptr(assigned), _lib.ptr(within))
+            out = _lib.RefineOutput(_lib.ptr(closest), _lib.ptr(mind), _lib.ptr(assigned), _lib.ptr(within), _lib.ptr(dmat))
             _lib.check(_lib.lib().dbb_refine_host(ctypes.byref(inp), ctypes.byref(out)))
         self.coreOrder = [c.binId for c in core_list]
         res = (closest, mind, assigned)
-        return res + (within[:, :B],) if want_within else res
+        if want_within:
+            res = res + (within[:, :B],)
+        if want_dist:
+            res = res + (dmat[:, :B],)
+        return res
 
     def refine(self, unbinnedContigs, cores, gcDist, gcDistPer, tdDist, tdDistPer, covDist, covDistPer):
         """What refineBins.py:60-96 + :172-175 leave behind: ``contig.binId`` of every unbinned contig is set to the

@@ -261,6 +261,7 @@ typedef struct {
   double* min_dist;            /* [U][3] the three minimum distances (1e9 if none); or NULL */
   int32_t* assigned;           /* [U] the core if the three agree, else -1; or NULL */
   uint8_t* within;             /* [U][B] bit0 GC, bit1 coverage, bit2 TD predicate (unbinned.py:137-152); or NULL */
+  double* dist;                /* [U][B] the L1 distance of every (contig, core) pair (compare.py:108,117); or NULL */
 } dbb_refine_output;
 
 int dbb_refine_dev(const dbb_refine_input* in, const dbb_refine_output* out, void* stream);

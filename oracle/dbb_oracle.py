@@ -667,6 +667,68 @@ def unbinned_table_literal(contigs, distributions, minScaffoldLen, minContigLen,
 
 
 # ----------------------------------------------------------------------------------------------
+# compare.py:70-152 (one scaffold against one bin; what `dbb compare` prints)
+# ----------------------------------------------------------------------------------------------
+
+def compare_text_literal(contigs, queryBinId, queryScaffoldId, distributions, numKmers=NUM_KMERS):
+    """compare.py:70-152 for ``contigs`` in the order compare.py meets them (binId -1 = unbinned: compare.py makes a bin
+    of those too, :88-90).  Bins are visited in order of first appearance.  Returns the text it prints."""
+    import re
+    queryContigs, queryBinContigs, bins = [], [], {}
+    for contig in contigs:
+        scaffoldId = contig.contigId
+        match = re.search('_c[0-9]*$', contig.contigId)
+        if match:
+            scaffoldId = contig.contigId[0:match.start()]
+        if scaffoldId == queryScaffoldId:
+            queryContigs.append(contig)
+        if contig.binId not in bins:
+            bins[contig.binId] = Core(contig.binId, 0, 0, 0, [0] * numKmers)
+        b = bins[contig.binId]
+        b.length += contig.length
+        weight = float(contig.length) / b.length
+        b.GC = contig.GC * weight + b.GC * (1.0 - weight)
+        b.coverage = contig.coverage * weight + b.coverage * (1.0 - weight)
+        for i in range(0, len(b.tetraSig)):
+            b.tetraSig[i] = contig.tetraSig[i] * weight + b.tetraSig[i] * (1.0 - weight)
+        if contig.binId == queryBinId:
+            queryBinContigs.append(contig)
+    sig_of = dict((k, np.asarray(v.tetraSig, dtype=np.float64)) for k, v in bins.items())
+    queryBin = bins[queryBinId]
+    meanDeltaTetra = np.mean([distance(c.tetraSig, sig_of[queryBinId]) for c in queryBinContigs])
+    out = ['\n', 'Contig Id\tGC\tCoverage\tdelta GC\tdelta Coverage\tdelta tetra\tWithin GC\tWithin coverage\tWithin tetra\t'
+           'Closest GC\tClosest coverage\tClosest tetra\n']
+    for contig in queryContigs:
+        tdDistanceQuery = distance(contig.tetraSig, sig_of[queryBinId])
+        bWithinGC = distributions.withinDistGC(contig, queryBin)
+        bWithinCov = distributions.withinDistCov(contig, queryBin)
+        bWithinTetra = distributions.witinDistTD(tdDistanceQuery, contig)
+        closestBin = [None] * 3
+        minDistances = [1e9] * 3
+        for binId, b in bins.items():
+            if not distributions.withinDistGC(contig, b):
+                continue
+            if not distributions.withinDistCov(contig, b):
+                continue
+            tdDistance = distance(contig.tetraSig, sig_of[binId])
+            if not distributions.witinDistTD(tdDistance, contig):
+                continue
+            distances = [abs(contig.GC - b.GC), abs(contig.coverage - b.coverage), tdDistance]      # compare.py:138
+            for i, d in enumerate(distances):
+                if d < minDistances[i]:
+                    minDistances[i] = d
+                    closestBin[i] = binId
+        out.append('%s\t%.1f\t%.1f\t%.1f\t%.1f\t%.2f\t%s\t%s\t%s\t%s\t%s\t%s\n' % (
+            contig.contigId, contig.GC * 100, contig.coverage, (contig.GC - queryBin.GC) * 100, contig.coverage - queryBin.coverage,
+            tdDistanceQuery, str(bool(bWithinGC)), str(bool(bWithinCov)), str(bool(bWithinTetra)), str(closestBin[0]), str(closestBin[1]),
+            str(closestBin[2])))
+    out.append('\n')
+    out.append('Bin Id = %s, mean GC = %.1f, mean coverage = %.1f, mean delta tetra = %.2f\n' % (queryBinId, queryBin.GC * 100,
+                                                                                            queryBin.coverage, meanDeltaTetra))
+    return ''.join(out)
+
+
+# ----------------------------------------------------------------------------------------------
 # N2: sequence side of preprocess -- splitScaffolds.py:27-53, seqUtils.py:258-265,
 # preprocess.py:94-100, :118-161 (what a worker computes from the sequence alone)
 # ----------------------------------------------------------------------------------------------

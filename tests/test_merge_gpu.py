@@ -166,3 +166,21 @@ def test_unbinned_table_random_instance_vs_literal_loop():
         want = O.unbinned_table_literal(contigs, dist, minS, minC, allScaffolds)
         assert got == want, allScaffolds
         assert len(want.split('\n')) > 500
+
+
+def test_compare_run_prints_the_reference_report(tmp_path, capsys):
+    """Compare.run through real files (compare.py:39) prints what the reference's own Compare.run printed."""
+    from dbb_b200.compare import Compare
+    from tests import util
+    cases = util.golden_json('ref_compare.json')
+    dirs = {}
+    for c in cases:
+        g, contigs, pr, gcDist, td, covDist = unbinned_case(c['case'])
+        if c['case'] not in dirs:
+            d = str(tmp_path / c['case'])
+            os.makedirs(d)
+            dirs[c['case']] = (d, _write_inputs(d, contigs, gcDist, td, covDist))
+        d, data = dirs[c['case']]
+        capsys.readouterr()
+        Compare().run(d, os.path.join(d, 'bins.tsv'), c['bin'], c['scaffold'], c['pers'][0], c['pers'][1], c['pers'][2], dataDir=data)
+        assert capsys.readouterr().out == c['stdout'], (c['case'], c['scaffold'])

@@ -248,3 +248,14 @@ def test_unbinned_oracle_matches_reference_outputs():
         g, contigs, pr, gcDist, td, covDist = unbinned_case(tag)
         dist = O.Distributions(gcDist, pr[0], td, pr[1], covDist, pr[2])
         assert O.unbinned_table_literal(contigs, dist, pr[3], pr[4], bool(pr[5])) == str(g[tag + '_unbinned_tsv']), tag
+
+
+def test_compare_oracle_matches_reference_outputs():
+    """compare.py: the literal restatement of :70-152 prints what the reference's own Compare.run printed (twelve
+    scaffold / bin queries over the two N6 cases, tests/golden/make_golden_compare.py)."""
+    cases = util.golden_json('ref_compare.json')
+    assert len(cases) == 12
+    for c in cases:
+        g, contigs, pr, gcDist, td, covDist = unbinned_case(c['case'])
+        dist = O.Distributions(gcDist, c['pers'][0], td, c['pers'][1], covDist, c['pers'][2])
+        assert O.compare_text_literal(contigs, c['bin'], c['scaffold'], dist) == c['stdout'], (c['case'], c['scaffold'])
