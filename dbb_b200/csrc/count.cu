@@ -396,6 +396,10 @@ int launch_class(const dbb_count_plan* plan, int cls, const void* d_codes, const
   int occ = 0;
   DBB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem));
   if (occ < 1) { dbb::set_error("count kernel S=%d does not fit on the device", S); return DBB_ERR_CUDA; }
+  // DBB_K1_OCC<S> caps the CTAs per SM of a class so that the class kernels share the SMs from the start instead of
+  // overlapping only at their tails (tuning switch; 0 = the occupancy limit)
+  static const int64_t cap = env_i64(S == 1 ? "DBB_K1_OCC1" : S == 2 ? "DBB_K1_OCC2" : S == 3 ? "DBB_K1_OCC3" : "DBB_K1_OCC4", 0);
+  if (cap > 0 && cap < occ) occ = (int)cap;
   uint32_t grid = (uint32_t)std::min<int64_t>((int64_t)occ * plan->sm_count, (int64_t)n);
   kern<<<grid, THREADS, smem, st>>>(plan->d_items + plan->class_begin[cls], n, plan->d_counters + cls,
                                     (const uint4*)d_codes, (const uint64_t*)d_valid, d_counts, d_freq,
