@@ -71,19 +71,26 @@ class Merge(object):
     def __init__(self, bDebug=False):
         self.logger = logging.getLogger()
 
+    @staticmethod
+    def binStatistics(binnedContigs):
+        """merge.py:66-92: the bins in visiting order (first appearance) with their running length-weighted statistics and
+        ``.contigs``.  Host side."""
+        cores = coreStatistics(binnedContigs)                 # insertion order = first appearance
+        bins = list(cores.values())
+        for b in bins:
+            b.contigs = []
+        for c in binnedContigs:
+            cores[c.binId].contigs.append(c)
+        return bins
+
     def mergeTable(self, binnedContigs, gcDist, gcDistPer, tdDist, tdDistPer, covDist, covDistPer, want_closest=False):
         """``binnedContigs``: objects with length, GC, coverage, tetraSig and a binId other than UNBINNED, in the order
         merge.py meets them.  Returns (bins, table[, closest]): ``bins`` the list of ``Core`` statistics in visiting
         order (``.contigs`` = the bin's contigs), ``table`` int32 [B][B][6] with, for source bin b1 and destination b2,
         the number of b1's contigs within the GC / coverage / TD distribution of b2 and the number whose closest valid
         bin in GC / TD / coverage space is b2 (merge.py:112-152); ``closest`` int32 [U][3] bin positions or -1."""
-        cores = coreStatistics(binnedContigs)                 # insertion order = first appearance
-        bins = list(cores.values())
+        bins = self.binStatistics(binnedContigs)
         pos = dict((b.binId, n) for n, b in enumerate(bins))
-        for b in bins:
-            b.contigs = []
-        for c in binnedContigs:
-            cores[c.binId].contigs.append(c)
         U, B = len(binnedContigs), len(bins)
         table = np.zeros((B, B, 6), dtype=np.int32)
         closest = np.full((U, 3), -1, dtype=np.int32) if want_closest else None

@@ -121,3 +121,48 @@ def test_all_gather_rows_gloo_world2():
     outs = [p.communicate(timeout=180)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), '\n'.join(outs)
     assert all('gloo ok' in o for o in outs)
+
+
+def test_merge_and_unbinned_host_sides_reproduce_the_reference_files_from_their_own_tables():
+    """Host logic of the N5 / N6 mirrors without a GPU: the running bin / scaffold statistics and the report formatting
+    of dbb_b200.merge / dbb_b200.unbinned, fed with the integer tables parsed back from the reference's own output
+    files, reproduce those files byte for byte."""
+    import re
+    from dbb_b200.merge import Merge
+    from dbb_b200.unbinned import Scaffold, Unbinned
+    from tests.test_oracle_golden import merge_case, unbinned_case
+    for tag in 'abc':
+        g, contigs, pers, _, _, _ = merge_case(tag)
+        text = str(g[tag + '_merge_tsv'])
+        bins = Merge.binStatistics([c for c in contigs if c.binId != -1])
+        pos = dict((b.binId, k) for k, b in enumerate(bins))
+        table = np.zeros((len(bins), len(bins), 6), dtype=np.int32)
+        for row in text.strip().split('\n')[1:]:
+            f = row.split('\t')
+            table[pos[f[0]], pos[f[3]]] = [int(x) for x in f[7:13]]
+        assert Merge().formatTable(bins, table) == text, tag
+    for tag in 'ab':
+        g, contigs, pr, _, _, _ = unbinned_case(tag)
+        text = str(g[tag + '_unbinned_tsv'])
+        minScaffoldLen, minContigLen, allScaffolds = pr[3], pr[4], bool(pr[5])
+        scaffolds, binned = {}, []
+        for c in contigs:                                              # unbinned.py:72-107
+            m = re.search('_c[0-9]*$', c.contigId)
+            sid = c.contigId[:m.start()] if m else c.contigId
+            if c.length < minContigLen:
+                continue
+            if c.binId != -1:
+                binned.append(c)
+            if c.binId == -1 or allScaffolds:
+                scaffolds.setdefault(sid, Scaffold(sid)).add(c)
+        scaffolds = list(scaffolds.values())
+        bins = Merge.binStatistics(binned)
+        spos = dict((s.scaffoldId, k) for k, s in enumerate(scaffolds))
+        bpos = dict((b.binId, k) for k, b in enumerate(bins))
+        table = np.zeros((len(scaffolds), len(bins), 7), dtype=np.int32)
+        for row in text.strip().split('\n')[1:]:
+            f = row.split('\t')
+            s = scaffolds[spos[f[0]]]
+            score = int(round(float(f[14]) * len(s.contigs)))
+            table[spos[f[0]], bpos[f[4]]] = [int(x) for x in f[8:14]] + [score]
+        assert Unbinned().formatTable(scaffolds, bins, table, minScaffoldLen) == text, tag
