@@ -436,6 +436,7 @@ def run_ours(args):
 
     # ---------------- parity spot check (untimed): sampled scaffolds / rows against the oracle ----------
     verified = None
+    oracle_check = None
     if rank == 0:
         from oracle import dbb_oracle as O
         rng = np.random.RandomState(0)
@@ -450,15 +451,33 @@ def run_ours(args):
             ok &= bool(np.array_equal(hc[i], O.seq_counts_np(s)))
         if not args.no_e2e:
             ok &= bool(np.array_equal(h_counts.astype(np.int64), hc))
-        if not counting_only and not args.no_prune:
-            # the pruned sweep against the full sweep of the same row block: identical, bit for bit
+        if not counting_only:
+            # stage 2 against the ORACLE at this size (every N, every workload): a seeded sample of this rank's rows,
+            # float64 distances to all n_total columns by the C restatement of tdNeighbours.py:41-51, predicates by the
+            # numpy restatement; top-k sets within the 2e-6 tie band, count / neighbour_bp exact outside it
+            from oracle import checks
             kn = result['knn']
-            ids = kn['row_ids']
-            full = device.pairs(sig_keep[0], dt, 0, n_total, k=K_NN,
-                                topk_filter=topk_filter, want_count=True) if n_total <= 300000 else None
-            if full is not None:
+            ids = kn['row_ids'].cpu().numpy() if 'row_ids' in kn else np.arange(r0, r1)
+            pos = np.sort(np.random.RandomState(1).choice(ids.shape[0], size=min(args.check_rows, ids.shape[0]), replace=False))
+            tpos = torch.from_numpy(pos).to(dev)
+            sig32 = sig_keep[0][:, :136].cpu().numpy()
+            c3 = args.workload == 'C3'
+            ot = O.DistTables(synthetic.synthetic_gc_dist() if c3 else None, TD_PER if c3 else None, load_td_dist(), TD_PER,
+                              synthetic.synthetic_cov_dist(seed=3) if c3 else None, TD_PER if c3 else None)
+            try:
+                oracle_check = checks.check_knn_sample(
+                    ids[pos], kn['idx'][tpos].cpu().numpy(), kn['dist'][tpos].cpu().numpy(), kn['count'][tpos].cpu().numpy(),
+                    kn['neighbour_bp'][tpos].cpu().numpy(), sig32, meta.length[order], K_NN, ot,
+                    GC=meta.gc_obs[order] if c3 else None, coverage=meta.coverage[order] if c3 else None, topk_filter_gc_cov=c3)
+            except AssertionError as exc:
+                raise SystemExit('bench.py: stage-2 parity check against the oracle FAILED: %s' % exc)
+            del sig32
+            if not args.no_prune and n_total <= 300000:
+                # additionally (cheap at these sizes): the pruned sweep against the full sweep, identical bit for bit
+                full = device.pairs(sig_keep[0], dt, 0, n_total, k=K_NN, topk_filter=topk_filter, want_count=True)
+                tid = kn['row_ids']
                 for key in ('idx', 'dist', 'count', 'neighbour_bp'):
-                    ok &= bool(torch.equal(kn[key], full[key][ids]))
+                    ok &= bool(torch.equal(kn[key], full[key][tid]))
         verified = ok
         if not ok:
             raise SystemExit('bench.py: parity spot check FAILED (counts differ from the oracle)')
@@ -528,7 +547,7 @@ def run_ours(args):
                        'dbb_tetra_signatures_host (pinned host buffers) + H2D of the signatures, device.pairs_pruned, D2H of the results'},
         'pruning': pruning,
         'gpu_launches': launches_per_step * args.steps, 'launches_per_step': launches_per_step,
-        'clocks': clocks, 'verified_vs_oracle': verified,
+        'clocks': clocks, 'verified_vs_oracle': verified, 'oracle_check_stage2': oracle_check,
         'shard': {'scaffolds_rank0': my_n, 'bp_rank0': my_bp, 'lpt_imbalance': parallel.imbalance(meta.length, parts),
                   'count_ms_per_rank': [round(r[0], 4) for r in per_rank], 'bp_per_rank': [int(r[1]) for r in per_rank],
                   'count_time_imbalance': max(r[0] for r in per_rank) / (sum(r[0] for r in per_rank) / len(per_rank))},
@@ -560,6 +579,7 @@ def main():
     ap.add_argument('--cpu-seconds', type=float, default=8.0, help='target wall time of each CPU-baseline leg')
     ap.add_argument('--no-cpu', action='store_true', help='skip the CPU baseline leg')
     ap.add_argument('--no-prune', action='store_true', help='stage 2 as a full sweep over all column tiles (default: exact tile skipping, device.pairs_pruned)')
+    ap.add_argument('--check-rows', type=int, default=96, help='rows of the all-pairs stage recomputed by the oracle after the timed region')
     ap.add_argument('--no-e2e', action='store_true', help='skip the host-buffer end-to-end leg (large exploratory workloads)')
     ap.add_argument('--workload', default='C2', choices=['C2', 'C3', 'C4', 'C5'], help='C2 = the benchmark of record (weak scaling); C3 = 250k scaffolds with GC + coverage filters, C4 = 1M scaffolds, C5 = 10M short contigs + 8 x 5 Mb, counting only (all strong scaling)')
     args = ap.parse_args()

@@ -80,26 +80,37 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // p = <sig, w> per scaffold (one warp per row, 35 x 128-bit loads) and its sort key (class * 4 + clamp(p, 0, 1): p is in
-// [0, 1], so classes do not interleave; a NaN signature sorts as p = 0 and is left out of the tile intervals)
+// [0, 1], so classes do not interleave; a NaN signature sorts as p = 0 and is left out of the tile intervals).
+// The bound L1(a, b) >= 2 |p_a - p_b| needs sum(a) = sum(b): in general L1 >= 2 |p_a - p_b| - |sum(a) - sum(b)|.  Both
+// sums are accumulated in FP64 here; a finite row whose sum is farther than sum_tol from 1 is counted in *bad_rows and
+// the caller refuses the plan (margin covers 2 * sum_tol plus the FP32 rounding of p).
 __global__ void __launch_bounds__(256) project_kernel(const float* __restrict__ sig, const float* __restrict__ w,
-                                                      const float* __restrict__ cls, int64_t n, float* __restrict__ p,
-                                                      uint32_t* __restrict__ key, int32_t* __restrict__ val) {
+                                                      const float* __restrict__ cls, int64_t n, float sum_tol, float* __restrict__ p,
+                                                      uint32_t* __restrict__ key, int32_t* __restrict__ val,
+                                                      unsigned long long* __restrict__ bad_rows) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= n) return;
   const float4* s = reinterpret_cast<const float4*>(sig + row * DBB_SIG_STRIDE);
   const float4* w4 = reinterpret_cast<const float4*>(w);
-  float acc = 0.f;
+  double acc = 0.0, tot = 0.0;
   for (int q = lane; q < DBB_SIG_STRIDE / 4; q += 32) {
     const float4 v = __ldg(s + q), x = __ldg(w4 + q);
-    acc += (v.x * x.x + v.y * x.y) + (v.z * x.z + v.w * x.w);
+    acc += ((double)v.x * x.x + (double)v.y * x.y) + ((double)v.z * x.z + (double)v.w * x.w);
+    tot += ((double)v.x + (double)v.y) + ((double)v.z + (double)v.w);
   }
-  acc = warp_sum(acc);
+  #pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    tot += __shfl_xor_sync(0xffffffffu, tot, d);
+  }
   if (lane == 0) {
-    p[row] = acc;
-    const float c = fminf(fmaxf(acc, 0.f), 1.f);                       // fmaxf(NaN, 0) = 0
+    const float pf = (float)acc;
+    p[row] = pf;
+    const float c = fminf(fmaxf(pf, 0.f), 1.f);                        // fmaxf(NaN, 0) = 0
     key[row] = __float_as_uint((cls ? cls[row] * 4.f : 0.f) + c);      // >= +0: the bit pattern is monotone
     val[row] = (int32_t)row;
+    if (tot == tot && !(fabs(tot - 1.0) <= (double)sum_tol)) atomicAdd(bad_rows, 1ull);
   }
 }
 
@@ -405,7 +416,10 @@ DBB_EXPORT int dbb_prune_plan_dev(const dbb_prune_input* in, const dbb_prune_buf
   float* p = (float*)(sc + L.p);
   uint32_t *key_in = (uint32_t*)(sc + L.key_in), *key_out = (uint32_t*)(sc + L.key_out);
   int32_t *val_in = (int32_t*)(sc + L.val_in), *perm = (int32_t*)(sc + L.val_out);
-  project_kernel<<<(unsigned)((in->n + 7) / 8), 256, 0, st>>>(in->sig, in->weights, in->cls, in->n, p, key_in, val_in);
+  DBB_REQUIRE(in->margin > 0.f, "margin must be positive");
+  DBB_CUDA_TRY(cudaMemsetAsync(buf->info + 4, 0, sizeof(int64_t), st));
+  project_kernel<<<(unsigned)((in->n + 7) / 8), 256, 0, st>>>(in->sig, in->weights, in->cls, in->n, 0.3f * in->margin, p, key_in, val_in,
+                                                             (unsigned long long*)(buf->info + 4));
   size_t cub_bytes = L.cub_bytes;
   DBB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(sc + L.cub_temp, cub_bytes, key_in, key_out, val_in, perm, (int)in->n, 0, 32, st));
   Tables ti = {in->length, in->td_bound, in->gc, in->gc_mbin, in->gc_lbin, in->cov, in->cov_lbin};

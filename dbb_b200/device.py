@@ -304,6 +304,10 @@ def pairs_pruned(sig_padded, dt, row0=0, row1=None, k=0, topk_filter=0, want_cou
         _lib.check(L.dbb_prune_second_dev(ctypes.byref(inp), ctypes.byref(b.struct), _p(kth), k, _stream()))
         launches += 6
     info = b.info.cpu().tolist()                                   # the one host read: list sizes of both plans
+    if info[4]:
+        raise _lib.DbbError('pairs_pruned: %d signature rows do not sum to 1 within %g: the tile-skipping bound '
+                            'L1 >= 2|p_a - p_b| does not hold for them (pass frequencies, or use the full sweep device.pairs)'
+                            % (info[4], 0.3 * margin))
     visited1, visited, n_aff = info[0], info[0], 0
     if second:
         visited, n_aff = info[0] + info[2], info[3]
@@ -366,7 +370,7 @@ def _prune_buffers(dt, n, row0, row1, world, dev):
     b.tl = torch.empty(max(n_slots * b.n_ct, 1), dtype=torch.int32, device=dev)
     b.cnt = torch.empty(b.n_rt, dtype=torch.int32, device=dev)
     b.mine = torch.zeros(b.n_rt, dtype=torch.uint8, device=dev)
-    b.info = torch.zeros(4, dtype=torch.int64, device=dev)
+    b.info = torch.zeros(8, dtype=torch.int64, device=dev)
     nbytes = int(_lib.lib().dbb_prune_scratch_bytes(n, rows, world))
     if nbytes < 0:
         _lib.check(-1)

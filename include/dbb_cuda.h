@@ -195,7 +195,8 @@ int dbb_pairs_host(const dbb_pairs_input* in_host, int64_t row0, int64_t row1,
  * Sorts the scaffolds by (class, p = <sig, weights>), carries the signature rows and per-scaffold tables into that
  * order, and writes the tile lists dbb_pairs_dev takes: a (row tile, column tile) pair is visited iff
  * 2 * gap(p intervals) - margin <= max(largest td_bound of the row tile, of the column tile)  [no td_bound: <= 0].
- * Exact for any weights in [0, 1] because signatures sum to 1: L1(a, b) >= 2 |p_a - p_b|.  Lists are ordered
+ * Exact for any weights in [0, 1] because signatures sum to 1: L1(a, b) >= 2 |p_a - p_b|.  PRECONDITION: every finite
+ * row of sig sums to 1 within 0.3 * margin (frequencies do; raw counts do not) -- checked on the device, see info[4].  Lists are ordered
  * nearest tile first.  world > 1: the row tiles are dealt to the ranks by decreasing list length; a rank's lists
  * cover its own row tiles only (mine[t] = 1).  All pointers are device pointers, caller-allocated. */
 typedef struct {
@@ -207,7 +208,7 @@ typedef struct {
   const double* cov; const int32_t* cov_lbin;     /* [n] each; NULL = absent */
   int64_t row0, row1;          /* rows of the SORTED order the sweep will cover */
   int32_t rank, world;         /* world <= 1: single GPU; else row0 = 0, row1 = n */
-  float margin;                /* slack of the FP32 projection, e.g. 1e-5 */
+  float margin;                /* slack: covers |sum(sig) - 1| <= 0.3 * margin of every row and the FP32 rounding of p; e.g. 1e-5 */
 } dbb_prune_input;
 
 typedef struct {
@@ -220,7 +221,9 @@ typedef struct {
   int32_t* tile_list;          /* capacity: row tiles of this rank x column tiles */
   int32_t* tile_count;         /* [row tiles] */
   uint8_t* mine;               /* [row tiles] */
-  int64_t* info;               /* [4]: tiles listed, row tiles with a non-empty list -- first plan, second plan */
+  int64_t* info;               /* [8]: [0..1] tiles listed, row tiles with a non-empty list -- first plan; [2..3] second plan;
+                                  [4] rows whose signature does not sum to 1 within 0.3 * margin (finite rows only): the
+                                  bound does not hold for them, the caller must refuse the plan's results if it is non-zero */
   void* scratch; int64_t scratch_bytes;   /* dbb_prune_scratch_bytes; must be left alone between the plan calls */
 } dbb_prune_buffers;
 

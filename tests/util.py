@@ -46,28 +46,4 @@ def check_mask_against_oracle(mask_rows, oracle_rows, d64=None, bound=None, atol
     return int(diff.sum())
 
 
-def check_topk(idx, dist, d64_rows, rows, k, allowed=None, atol=DIST_ATOL):
-    """GPU top-k (idx, dist) vs float64 distance rows: distances within atol of float64, and the index
-    set equal to the oracle's up to swaps among candidates within atol of the oracle's k-th distance."""
-    n = d64_rows.shape[1]
-    for r, i in enumerate(rows):
-        ok = ~np.isnan(d64_rows[r])
-        ok[i] = False
-        if allowed is not None:
-            ok &= allowed[r].astype(bool)
-        cand = np.nonzero(ok)[0]
-        m = min(k, cand.size)
-        got = idx[r]
-        assert (got[m:] == -1).all() and np.isinf(dist[r][m:]).all(), 'row %d: padding' % i
-        got = got[:m]
-        assert len(set(got.tolist())) == m and ok[got].all(), 'row %d: invalid/duplicate neighbours' % i
-        assert np.abs(dist[r][:m] - d64_rows[r][got]).max(initial=0) <= atol, 'row %d: distance error' % i
-        assert (np.diff(dist[r][:m]) >= 0).all(), 'row %d: not sorted' % i
-        if m == 0:
-            continue
-        order = cand[np.lexsort((cand, d64_rows[r][cand]))]
-        kth = d64_rows[r][order[m - 1]]
-        must = set(order[d64_rows[r][order] < kth - atol].tolist())        # clearly inside
-        may = set(order[d64_rows[r][order] <= kth + atol].tolist())        # inside or in the tie band
-        g = set(got.tolist())
-        assert must <= g <= may, 'row %d: neighbour set differs beyond the tie band' % i
+from oracle.checks import check_topk   # noqa: E402,F401  (shared with bench.py's parity check)
