@@ -94,6 +94,7 @@ SIGNATURES = {
     'dbb_count_plan_create': (ctypes.c_int, [c_vp, c_i64, ctypes.POINTER(c_vp)]),
     'dbb_count_plan_destroy': (ctypes.c_int, [c_vp]),
     'dbb_count_plan_launches': (ctypes.c_int, [c_vp]),
+    'dbb_count_class_limits': (ctypes.c_int, [c_vp]),
     'dbb_tetra_count_dev': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
     'dbb_tetra_signatures_host': (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
     'dbb_pairs_dev': (ctypes.c_int, [ctypes.POINTER(PairsInput), c_i64, c_i64, ctypes.POINTER(PairsOutput), c_vp]),
@@ -126,9 +127,10 @@ def lib():
     GenomicSignatures, preprocess.py:395-413, so nothing CUDA may happen at import/__init__ time)."""
     global _LIB
     if _LIB is None:
-        if not os.path.exists(LIB_PATH):
-            raise DbbError('%s is not built (run `python -m dbb_b200.build`); dbb_b200 has no CPU fallback' % LIB_PATH)
-        L = ctypes.CDLL(os.environ.get('DBB_LIB_PATH', LIB_PATH))   # override: A/B runs of two builds
+        path = os.environ.get('DBB_LIB_PATH', LIB_PATH)             # override: A/B runs of two builds
+        if not os.path.exists(path):
+            raise DbbError('%s is not built (run `python -m dbb_b200.build`); dbb_b200 has no CPU fallback' % path)
+        L = ctypes.CDLL(path)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(L, name)
             fn.restype = res

@@ -4,23 +4,30 @@
 // window that contains a byte outside {A,C,G,T}, increment the canonical column, then divide by the
 // sum (0/0 -> NaN).  The integer counts must be bit-exact.
 //
-// Hardware facts this design follows (profiles/microbench/, measured on B200):
-//   * shared-memory atomics (ATOMS.POPC.INC) retire ~11.7 random updates / clk / SM no matter how the
-//     histogram is replicated (16-18 when made bank-conflict-free at 32x the flush cost), i.e. one
-//     atomic per WINDOW caps the kernel near 30 % of HBM bandwidth;
-//   * so one atomic covers S windows: a (3+S)-mer histogram (4^(3+S) bins) is updated once every S
-//     bases ("super-k-mer"), and folded to the 256 tetramer codes when the scaffold ends.  S=2/3/4
-//     measured 21.5 / 32 / 42 windows/clk/SM.  The fold is exact integer arithmetic:
-//         count4[c] = sum over window offsets o < S of the marginal of the (3+S)-mer histogram.
-//   * the fold + re-zero costs O(4^(3+S)) shared-memory cycles per scaffold, so S is chosen per
-//     scaffold from its length (short contigs S=1 ... megabase scaffolds S=4).
+// Hardware facts this design follows (profiles/microbench/mb2.cu, mb4.cu, measured on B200):
+//   * the SM's shared-memory pipe retires one wavefront per clock; a shared-memory atomic of 32 random bins costs
+//     ~3-3.7 wavefronts (bank conflicts of random addresses), so one atomic per WINDOW caps counting near 9-12
+//     windows / clk / SM, a quarter of what the HBM target needs;
+//   * so one atomic covers S windows: a (3+S)-mer histogram (4^(3+S) bins) is updated once every S bases
+//     ("super-k-mer") and folded to the 256 tetramer codes when the scaffold ends.  The fold is exact integer
+//     arithmetic:  count4[c] = sum over window offsets o < S of the marginal of the (3+S)-mer histogram.
+//     Measured ceilings without the fold (mb4, 16-bit counters): 17 / 26 / 35 / 38 windows / clk / SM for S = 2..5 on
+//     uniform sequence, 14 / 22 / 31 / 33 on a 30 % GC genome (skewed bins collide more);
+//   * the fold costs O(4^(3+S)) wavefronts per scaffold, so S is chosen per scaffold from its length.
 //
-// Work decomposition: a work ITEM is a run of 64-base blocks of one scaffold (whole scaffold, or a
-// chunk of a very long one); one CTA owns one item at a time and one histogram.  Lane i of a warp
-// loads block i with a single 128-bit load (512 contiguous bytes per warp), the 3..6-base halo of the
-// next block arrives by warp shuffle.  Windows whose super-k-mer is only partly valid (N, lowercase,
-// scaffold end) take a rare per-window path.  Whole-scaffold items write counts and frequencies
-// directly; chunks of split scaffolds add into a scratch row that a finalize kernel normalises.
+// Round 2 layout: ONE WARP owns one work item and one histogram; nothing in the kernel synchronises wider than a
+// warp, so a warp that folds or writes its outputs never stalls the atomics of the others (round 1 used one CTA per
+// item and lost 3-5 issue slots per instruction to barriers around the fold).  Counters are 16 bits wide, two per
+// 32-bit word (word = bin without its top bit, half = the top bit): the histogram of S = 4 is 32 KB instead of 64 KB,
+// six of them fit an SM, every fold reads and re-zeroes half the bytes; an item is at most 65 535 super-k-mers
+// (4 095 blocks for S = 4), so no counter can wrap.
+//
+// Work decomposition: a work ITEM is a run of 64-base blocks of one scaffold (whole scaffold, or a chunk of a very
+// long one).  Lane i of the warp loads block i of the current 32-block stripe with a single 128-bit load (512
+// contiguous bytes per warp), the halo of the next block arrives by warp shuffle, loads run DEPTH stripes ahead of
+// the atomics.  Windows whose super-k-mer is only partly valid (N, lowercase, scaffold end) take a rare per-window
+// path.  Whole-scaffold items write counts and frequencies directly; chunks of split scaffolds add into a scratch row
+// that a finalize kernel normalises.
 #include "common.cuh"
 #include <algorithm>
 #include <cstdlib>
@@ -43,48 +50,85 @@ __constant__ int16_t c_col_code1[DBB_NUM_KMERS];
 __constant__ int16_t c_col_code2[DBB_NUM_KMERS];
 __constant__ int c_debug_skip_flush = 0;   // profiling switch (DBB_K1_DEBUG_SKIP_FLUSH=1): count only, no fold / output
 
-template <int THREADS>
-__device__ __forceinline__ void group_sync() {
-  if (THREADS == 32) __syncwarp(); else __syncthreads();
+template <int S> struct Geo {
+  static constexpr int R = S + 3;                       // bases per super-k-mer
+  static constexpr int KB = 2 * R;                      // bits per bin index
+  static constexpr int BINS = 1 << KB;
+  static constexpr int WORDS = S == 1 ? 0 : BINS / 2;   // 16-bit counters, two per word (S = 1 counts straight into c4)
+};
+
+// All shared memory of the kernel is the dynamic array below, addressed by WORD OFFSETS (not by derived pointers:
+// a generic pointer into shared memory costs an S2UR + ULEA to build every time it is materialised, which was 30 % of
+// the warp time of the short-contig class).  Layout per CTA: c4[256] u32 | histogram[WORDS] | column table[160] |
+// WPI x slow-path scratch[16].
+extern __shared__ __align__(16) uint32_t smem[];
+constexpr int OFF_C4 = 0;
+constexpr int OFF_HS = 256;
+
+// Shared-memory accesses by 32-bit shared-space BYTE address (the address of smem[] is taken once per thread; the
+// compiler otherwise rebuilds the CTA's shared window -- S2UR SR_CgaCtaId + ULEA -- in every basic block that
+// touches shared memory).
+__device__ __forceinline__ uint32_t lds(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v; asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v;
+}
+__device__ __forceinline__ void sts(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts128_zero(uint32_t a) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void red_add(uint32_t a, uint32_t v) { asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void red_inc(uint32_t a) { asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a) : "memory"); }
+
+// one update of the (3+S)-mer histogram; x holds the bin in bits [2, 2 + KB)
+template <int S>
+__device__ __forceinline__ void bump(uint32_t sb, uint32_t x) {
+  constexpr int KB = Geo<S>::KB;
+  if (S == 1) {
+    red_inc(sb + (x & (255u << 2)));
+  } else {
+    constexpr uint32_t WMASK4 = ((1u << (KB - 1)) - 1u) << 2;     // byte offset of the word: the bin without its top bit
+    constexpr uint32_t TOP = 1u << (KB + 1);                       // top bit of the bin selects the half
+    red_add(sb + 4 * OFF_HS + (x & WMASK4), (x & TOP) ? 0x10000u : 1u);
+  }
 }
 
 // Rare path: blocks that are not fully valid (N / IUPAC / lowercase, the padded last block of a scaffold, a
 // block whose halo is invalid).  The warp handles them one at a time and COOPERATIVELY: the owning lane
 // publishes the block through a 10-word shared scratch, lane a then treats anchor a (a, a+32 for S = 1).  A
 // fully valid anchor still updates the (3+S)-mer histogram; otherwise its valid windows go one by one to the
-// tetramer histogram.  ~60 instructions per slow block instead of ~1000 for a per-lane loop over anchors.
+// tetramer histogram.
 template <int S>
 __device__ __noinline__ void slow_blocks(uint32_t slowmask, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3,
-                                         uint32_t w4, uint64_t V, uint32_t Vh, int n_anchor,
-                                         volatile uint32_t* sc, uint32_t* hS, uint32_t* c4, int lane) {
-  constexpr int R = S + 3;
-  constexpr int KB = 2 * R;
+                                         uint32_t w4, uint64_t V, uint32_t Vh, int n_anchor, uint32_t sb, int off_sc, int lane) {
+  constexpr int R = Geo<S>::R;
+  constexpr int KB = Geo<S>::KB;
+  const uint32_t sc = sb + 4 * off_sc;
   while (slowmask) {
     const int src = __ffs(slowmask) - 1;
     slowmask &= slowmask - 1;
     if (lane == src) {
-      sc[0] = w0; sc[1] = w1; sc[2] = w2; sc[3] = w3; sc[4] = w4; sc[5] = 0u;
-      sc[6] = (uint32_t)(V >> 32); sc[7] = (uint32_t)V; sc[8] = Vh; sc[9] = (uint32_t)n_anchor;
+      sts(sc, w0); sts(sc + 4, w1); sts(sc + 8, w2); sts(sc + 12, w3); sts(sc + 16, w4); sts(sc + 20, 0u);
+      sts(sc + 24, (uint32_t)(V >> 32)); sts(sc + 28, (uint32_t)V); sts(sc + 32, Vh); sts(sc + 36, (uint32_t)n_anchor);
     }
     __syncwarp();
-    const uint64_t V64 = ((uint64_t)sc[6] << 32) | sc[7];
-    const uint32_t vh = sc[8];
-    const int na = (int)sc[9];
+    const uint64_t V64 = ((uint64_t)lds(sc + 24) << 32) | lds(sc + 28);
+    const uint32_t vh = lds(sc + 32);
+    const int na = (int)lds(sc + 36);
     for (int a = lane; a < na; a += 32) {
       const int p = a * S;
       // validity of positions p, p+1, ... in the top bits of x
       const uint64_t x = (V64 << p) | (p ? (((uint64_t)vh << 32) >> (64 - p)) : 0ull);
       const int k = p >> 4, o = p & 15;
       if ((x >> (64 - R)) == ((1ull << R) - 1ull)) {
-        const uint64_t pair = ((uint64_t)sc[k] << 32) | sc[k + 1];
-        atomicAdd(&hS[(uint32_t)(pair >> (64 - 2 * o - KB)) & ((1u << KB) - 1u)], 1u);
+        const uint64_t pair = ((uint64_t)lds(sc + 4 * k) << 32) | lds(sc + 4 * k + 4);
+        bump<S>(sb, ((uint32_t)(pair >> (64 - 2 * o - KB)) & ((1u << KB) - 1u)) << 2);
       } else {
         #pragma unroll
         for (int o2 = 0; o2 < S; ++o2) {
           if (((x >> (60 - o2)) & 15ull) == 15ull) {
             const int q = p + o2, k2 = q >> 4, oq = q & 15;
-            const uint64_t pair = ((uint64_t)sc[k2] << 32) | sc[k2 + 1];
-            atomicAdd(&c4[(uint32_t)(pair >> (64 - 2 * oq - 8)) & 255u], 1u);
+            const uint64_t pair = ((uint64_t)lds(sc + 4 * k2) << 32) | lds(sc + 4 * k2 + 4);
+            red_inc(sb + 4 * (OFF_C4 + ((uint32_t)(pair >> (64 - 2 * oq - 8)) & 255u)));
           }
         }
       }
@@ -94,14 +138,12 @@ __device__ __noinline__ void slow_blocks(uint32_t slowmask, uint32_t w0, uint32_
 }
 
 // Fast path of one 64-base block whose bases (and the R-1 halo bases) are all valid: one unpredicated
-// shared-memory atomic per anchor -- funnel shift, mask, ATOMS: 3 instructions per S windows.
+// shared-memory atomic per anchor.
 //   w0..w3: code words of the block, w4: first code word of the next block (halo)
 //   n_anchor: super-k-mers anchored in this block (64/S; 21 or 22 for S = 3)
 template <int S>
-__device__ __forceinline__ void fast_block(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4,
-                                           int n_anchor, uint32_t* hS) {
-  constexpr int KB = 2 * (S + 3);
-  constexpr uint32_t BINMASK4 = ((1u << KB) - 1u) << 2;
+__device__ __forceinline__ void fast_block(uint32_t sb, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4, int n_anchor) {
+  constexpr int KB = Geo<S>::KB;
   constexpr int NA = (64 + S - 1) / S;                 // 64, 32, 22, 16
   const uint32_t w[5] = {w0, w1, w2, w3, w4};
   #pragma unroll
@@ -110,7 +152,7 @@ __device__ __forceinline__ void fast_block(uint32_t w0, uint32_t w1, uint32_t w2
     const int sh = 64 - 2 * o - KB - 2;                // >= 18
     const uint32_t x = (sh >= 32) ? (w[k] >> (sh - 32)) : __funnelshift_r(w[k + 1], w[k], sh);
     if (S == 3 && p == 63 && n_anchor != NA) continue; // S = 3: the anchor at 63 may belong to the next block
-    atomicAdd(reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(hS) + (x & BINMASK4)), 1u);
+    bump<S>(sb, x);
   }
 }
 
@@ -120,30 +162,102 @@ __device__ __forceinline__ bool block_all_valid(uint64_t V, uint32_t Vh) {
   return (V == ~0ull) && ((Vh & HALO) == HALO);
 }
 
-template <int S, int THREADS>
-__global__ void __launch_bounds__(THREADS) count_kernel(const Item* __restrict__ items, uint32_t n_items,
-                                                        uint32_t* __restrict__ next_item,
-                                                        const uint4* __restrict__ codes,
-                                                        const uint64_t* __restrict__ valid,
-                                                        uint32_t* __restrict__ counts,
-                                                        float* __restrict__ freq, int64_t freq_stride,
-                                                        uint32_t* __restrict__ split_counts) {
-  constexpr int BINS = 1 << (2 * (3 + S));
-  extern __shared__ uint32_t smem[];
-  uint32_t* c4 = smem;                                   // [256]
-  uint32_t* hS = (S == 1) ? smem : smem + 256;           // [BINS] (aliases c4 when S == 1)
-  __shared__ uint32_t s_item;
-  __shared__ uint32_t s_total[THREADS / 32];
-  __shared__ uint32_t s_slow[THREADS / 32][10];
-  const int tid = threadIdx.x, lane = tid & 31;
+__device__ __forceinline__ uint32_t halves(uint32_t v) { return (v & 0xffffu) + (v >> 16); }
+__device__ __forceinline__ uint32_t sum4(const uint4& v) { return (v.x + v.y) + (v.z + v.w); }   // packed: no half can wrap
 
-  for (int i = tid; i < (S == 1 ? 256 : 256 + BINS); i += THREADS) smem[i] = 0;
-  group_sync<THREADS>();
+// Fold of the CTA's (3+S)-mer histogram into its 256 tetramer codes.  Thread <-> code: warp w takes the codes
+// c = lane + 32 q of its q's; no shuffles.  Bin = (b0 .. b_{R-1}), b0 most significant; word = bin without its top bit,
+// low / high half = top bit 0 / 1.  For window offset o the count of code c = (b_o .. b_{o+3}) is the sum over the o
+// bases before it and the e = S-1-o bases after it:
+//   o = 0 : the top bit belongs to the code -- the codes c and c | 128 share their words (low / high halves); a run of
+//           4^e consecutive words each;
+//   o >= 1: the top bit belongs to the summed prefix -- both halves of every word are added; 4^o / 2 runs of 4^e words.
+// Runs of >= 4 words are read as 128-bit words in an order rotated by the lane so that the eight lanes of a
+// 128-bit wavefront hit eight different 16-byte bank groups.
+template <int S, int WPI>
+__device__ __forceinline__ void fold_histogram(uint32_t sb, int lane, int warp) {
+  #pragma unroll
+  for (int o = 0; o < S; ++o) {
+    const int e = S - 1 - o;                    // bases after the window
+    const int run = 1 << (2 * e);               // consecutive words per run
+    const int nq = run >> 2;                    // 128-bit chunks per run (0: single words)
+    if (o == 0) {
+      #pragma unroll 1
+      for (int q = warp; q < 4; q += WPI) {
+        const int c = lane + 32 * q;            // < 128: low halves -> code c, high halves -> code c | 128
+        const int base = OFF_HS + (c << (2 * e));
+        uint32_t s = 0;
+        if (nq == 0) {
+          s = lds(sb + 4 * base);
+        } else {
+          #pragma unroll
+          for (int r4 = 0; r4 < nq; ++r4) {
+            const int ch = nq == 4 ? ((r4 + (lane >> 1)) & 3) : ((r4 + lane) & (nq - 1));
+            s += sum4(lds128(sb + 4 * (base + 4 * ch)));
+          }
+        }
+        red_add(sb + 4 * (OFF_C4 + c), s & 0xffffu);
+        red_add(sb + 4 * (OFF_C4 + c + 128), s >> 16);
+      }
+    } else {
+      const int npfx = 1 << (2 * o - 1);        // prefix values without the top bit
+      #pragma unroll 1
+      for (int q = warp; q < 8; q += WPI) {
+        const int c = lane + 32 * q;
+        uint32_t s = 0;
+        #pragma unroll 4
+        for (int pfx = 0; pfx < npfx; ++pfx) {
+          const int base = OFF_HS + ((pfx << (8 + 2 * e)) | (c << (2 * e)));
+          if (nq == 0) {
+            s += lds(sb + 4 * base);
+          } else {
+            #pragma unroll
+            for (int r4 = 0; r4 < nq; ++r4) {
+              const int ch = nq == 4 ? ((r4 + (lane >> 1)) & 3) : ((r4 + lane) & (nq - 1));
+              s += sum4(lds128(sb + 4 * (base + 4 * ch)));
+            }
+          }
+        }
+        red_add(sb + 4 * (OFF_C4 + c), halves(s));
+      }
+    }
+  }
+}
 
-  // Static schedule: CTA b takes items b, b + grid, ... of a list sorted by descending size, so every load of
-  // the pipeline below is known one step ahead: the first block of the NEXT item is requested before the
-  // current item is flushed, the next iteration's blocks before the current ones are processed.
-  struct Fetch { uint4 c; uint64_t V; uint32_t hw, hv; };
+template <int WPI>
+__device__ __forceinline__ void group_sync() {
+  if (WPI == 1) __syncwarp(); else __syncthreads();
+}
+
+// this lane's block of a stripe, loaded one stripe ahead of its use
+struct Fetch { uint4 c; uint64_t V; uint32_t hw, hv; };
+
+template <int S, int WPI, int MINB>
+__global__ void __launch_bounds__(32 * WPI, MINB) count_kernel(const Item* __restrict__ items, uint32_t n_items,
+                                                               const uint4* __restrict__ codes,
+                                                               const uint64_t* __restrict__ valid,
+                                                               uint32_t* __restrict__ counts,
+                                                               float* __restrict__ freq, int64_t freq_stride,
+                                                               uint32_t* __restrict__ split_counts) {
+  // One CTA = the WPI warps that share one item and one histogram (a warp is latency-bound around its atomics, so a
+  // histogram needs several warps to keep the shared-memory pipe fed; the warps only meet at the end of an item).
+  constexpr int WORDS = Geo<S>::WORDS;
+  constexpr int OFF_CC = 256 + WORDS;                     // column table: the (one or two) codes of column i, 16 bits each
+  constexpr int OFF_SC = OFF_CC + 160;                    // slow-path scratch, 16 words per warp
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t sb = (uint32_t)__cvta_generic_to_shared(smem);
+  for (int i = threadIdx.x; i < OFF_SC + 16 * WPI; i += 32 * WPI) {
+    uint32_t v = 0;
+    const int col = i - OFF_CC;
+    if (col >= 0 && col < 160)
+      v = col < DBB_NUM_KMERS ? ((uint32_t)(uint16_t)c_col_code1[col] | ((uint32_t)(uint16_t)c_col_code2[col] << 16)) : 0xffffffffu;
+    sts(sb + 4 * i, v);
+  }
+  group_sync<WPI>();
+
+  // Static schedule: CTA g takes items g, g + G, ... of a list sorted by descending size, so every load below is
+  // known one step ahead: the next stripe (of this item or of the next one) is requested before the current one is
+  // processed, the record of the item after the next when an item begins.
   auto fetch = [&](const Item& im, uint32_t b) {
     Fetch f;
     f.c = make_uint4(0, 0, 0, 0); f.V = 0; f.hw = 0; f.hv = 0;
@@ -161,15 +275,7 @@ __global__ void __launch_bounds__(THREADS) count_kernel(const Item* __restrict__
     }
     return f;
   };
-  (void)next_item; (void)s_item;
-  constexpr int NCOLT = (DBB_SIG_STRIDE + THREADS - 1) / THREADS;   // output columns per thread (136 + 4 padding)
-  int cc1[NCOLT], cc2[NCOLT];
-  #pragma unroll
-  for (int q = 0; q < NCOLT; ++q) {
-    const int col = tid + q * THREADS;
-    cc1[q] = col < DBB_NUM_KMERS ? c_col_code1[col] : -1;
-    cc2[q] = col < DBB_NUM_KMERS ? c_col_code2[col] : -1;
-  }
+  const uint32_t tid = threadIdx.x;
   uint32_t it = blockIdx.x;
   Item item = Item{0, 0, 0, 0};
   Fetch nxt;
@@ -178,18 +284,17 @@ __global__ void __launch_bounds__(THREADS) count_kernel(const Item* __restrict__
 
   while (it < n_items) {
     const uint32_t it_n = it + gridDim.x;
-    const bool has_n = it_n < n_items;
+    const bool has_n = it_n < n_items && it_n > it;
     Item item_n = Item{0, 0, 0, 0};
     if (has_n) item_n = items[it_n];
     const uint32_t nb = item.n_blocks;
-    const uint32_t slot = item.flags & ITEM_SLOT_MASK;
     const uint32_t first_mod3 = (item.flags >> 29) & 3u;
 
-    for (uint32_t base = 0; base < nb || base == 0; base += THREADS) {
+    for (uint32_t base = 0; base < nb || base == 0; base += 32 * WPI) {
       const uint32_t b = base + tid;
       const bool act = b < nb;
       const Fetch cur = nxt;
-      if (base + THREADS < nb) nxt = fetch(item, base + THREADS + tid);
+      if (base + 32 * WPI < nb) nxt = fetch(item, base + 32 * WPI + tid);
       else if (has_n) nxt = fetch(item_n, tid);
       const uint4 c = cur.c;
       const uint64_t V = cur.V;
@@ -214,96 +319,62 @@ __global__ void __launch_bounds__(THREADS) count_kernel(const Item* __restrict__
         n_anchor = p0 == 0 ? 22 : 21;
       }
       const bool ok = act && block_all_valid<S>(Vb, hvb);
-      if (ok) fast_block<S>(w0, w1, w2, w3, w4, n_anchor, hS);
+      if (ok) fast_block<S>(sb, w0, w1, w2, w3, w4, n_anchor);
       const uint32_t slow = __ballot_sync(0xffffffffu, act && !ok);
-      if (slow) slow_blocks<S>(slow, w0, w1, w2, w3, w4, Vb, hvb, n_anchor, s_slow[tid >> 5], hS, c4, lane);
+      if (slow) slow_blocks<S>(slow, w0, w1, w2, w3, w4, Vb, hvb, n_anchor, sb, OFF_SC + 16 * warp, lane);
     }
-    group_sync<THREADS>();
-    if (c_debug_skip_flush) { it = it_n; item = item_n; continue; }
+    group_sync<WPI>();
+    if (c_debug_skip_flush) { it = it_n; item = item_n; if (!has_n) break; continue; }
 
     if (S > 1) {
-      // Fold the (3+S)-mer histogram into the 256 tetramer codes: for window offset o the count of code c is
-      // the marginal over the o bases before and the S-1-o bases after it.  Thread <-> code, so no atomics
-      // are needed (two thread groups split the offsets when the CTA has >= 512 threads); runs of >= 4 bins
-      // are read as 128-bit words, rotated by the code so that neighbouring lanes hit different banks.
-      constexpr int NPART = THREADS >= 512 ? 2 : 1;
-      const int part = tid >> 8;
-      if (part < NPART) {
-        for (int c = tid & 255; c < 256; c += (THREADS < 256 ? THREADS : 256)) {
-          uint32_t sum = 0;
-          #pragma unroll
-          for (int o = 0; o < S; ++o) {
-            if (NPART == 2 && (o & 1) != part) continue;
-            constexpr int dummy = 0; (void)dummy;
-            const int e = S - 1 - o;                  // bases after the window
-            const int run = 1 << (2 * e);             // consecutive bins per prefix value
-            const int np = 1 << (2 * o);              // prefix values
-            #pragma unroll
-            for (int pfx = 0; pfx < np; ++pfx) {
-              const int base = (pfx << (8 + 2 * e)) | (c << (2 * e));
-              if (run >= 4) {
-                const int nq = run >> 2;
-                #pragma unroll
-                for (int r4 = 0; r4 < nq; ++r4) {
-                  const uint4 v = *reinterpret_cast<const uint4*>(hS + base + 4 * ((r4 + c) & (nq - 1)));
-                  sum += (v.x + v.y) + (v.z + v.w);
-                }
-              } else {
-                sum += hS[base];
-              }
-            }
-          }
-          if (NPART == 2) atomicAdd(&c4[c], sum); else c4[c] += sum;
-        }
-      }
-      group_sync<THREADS>();
-      for (int x = tid * 4; x < BINS; x += THREADS * 4) *reinterpret_cast<uint4*>(hS + x) = make_uint4(0, 0, 0, 0);
-      // (the next item's first update is behind the two group_syncs below)
+      fold_histogram<S, WPI>(sb, lane, warp);
+      group_sync<WPI>();                                    // every marginal is in c4, nobody reads the histogram any more
+      for (int x = tid * 4; x < WORDS; x += 128 * WPI) sts128_zero(sb + 4 * (OFF_HS + x));
     }
 
-    // canonical fold 256 -> 136 (column tables in registers), total = sum of the folded counts, one
-    // reciprocal per scaffold: freq = (float)(n * (1.0 / total))  (0 * inf = NaN when nothing was counted,
-    // as genomicSignatures.py:147-148 yields)
+    // canonical fold 256 -> 136 by warp 0, total = sum of the folded counts, one reciprocal per scaffold:
+    // freq = (float)(n * (1.0 / total))  (0 * inf = NaN when nothing was counted, as genomicSignatures.py:147-148 yields)
+    constexpr int NCOLT = (DBB_SIG_STRIDE + 31) / 32;       // output columns per lane (136 + 4 padding)
     uint32_t nloc[NCOLT];
     uint32_t part = 0;
-    #pragma unroll
-    for (int q = 0; q < NCOLT; ++q) {
-      uint32_t nq = 0;
-      if (cc1[q] >= 0) { nq = c4[cc1[q]]; if (cc2[q] >= 0) nq += c4[cc2[q]]; }
-      nloc[q] = nq;
-      part += nq;
-    }
-    #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
-    if (THREADS > 32) {
-      if (lane == 0) s_total[tid >> 5] = part;
-      __syncthreads();
-      part = 0;
+    if (warp == 0) {
       #pragma unroll
-      for (int i = 0; i < THREADS / 32; ++i) part += s_total[i];
-    } else {
+      for (int q = 0; q < NCOLT; ++q) {
+        const uint32_t cc = lds(sb + 4 * (OFF_CC + lane + 32 * q));
+        uint32_t nq = 0;
+        if (cc != 0xffffffffu) { nq = lds(sb + 4 * (OFF_C4 + (cc & 0xffffu))); if (!(cc >> 31)) nq += lds(sb + 4 * (OFF_C4 + (cc >> 16))); }
+        nloc[q] = nq;
+        part += nq;
+      }
+      #pragma unroll
+      for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
       __syncwarp();
-    }
-    // every thread has read its c4 entries: re-zero for the next item (its first update is behind the final sync)
-    for (int i = tid; i < 256; i += THREADS) c4[i] = 0;
-    const uint32_t total = part;
-    if (slot == 0) {
-      const double inv = 1.0 / (double)total;
+      // every lane has read its c4 entries: re-zero for the next item (its first update is behind the sync below)
       #pragma unroll
-      for (int q = 0; q < NCOLT; ++q) {
-        const int col = tid + q * THREADS;
-        if (col < DBB_NUM_KMERS && counts) counts[(size_t)item.scaffold * DBB_NUM_KMERS + col] = nloc[q];
-        if (freq && col < (int)freq_stride)
-          freq[(size_t)item.scaffold * freq_stride + col] = col < DBB_NUM_KMERS ? (float)((double)nloc[q] * inv) : 0.f;
-      }
-    } else {
-      #pragma unroll
-      for (int q = 0; q < NCOLT; ++q) {
-        const int col = tid + q * THREADS;
-        if (col < DBB_NUM_KMERS && nloc[q]) atomicAdd(&split_counts[(size_t)(slot - 1) * DBB_NUM_KMERS + col], nloc[q]);
+      for (int i = 0; i < 2; ++i) sts128_zero(sb + 4 * (OFF_C4 + 4 * lane + 128 * i));
+    }
+    group_sync<WPI>();                                      // histogram and c4 are zero again: the next item may start
+    if (warp == 0) {
+      const uint32_t total = part;
+      const uint32_t slot = item.flags & ITEM_SLOT_MASK;
+      if (slot == 0) {
+        const double inv = 1.0 / (double)total;
+        #pragma unroll
+        for (int q = 0; q < NCOLT; ++q) {
+          const int col = lane + q * 32;
+          if (col < DBB_NUM_KMERS && counts) counts[(size_t)item.scaffold * DBB_NUM_KMERS + col] = nloc[q];
+          if (freq && col < (int)freq_stride)
+            freq[(size_t)item.scaffold * freq_stride + col] = col < DBB_NUM_KMERS ? (float)((double)nloc[q] * inv) : 0.f;
+        }
+      } else {
+        #pragma unroll
+        for (int q = 0; q < NCOLT; ++q) {
+          const int col = lane + q * 32;
+          if (col < DBB_NUM_KMERS && nloc[q]) atomicAdd(&split_counts[(size_t)(slot - 1) * DBB_NUM_KMERS + col], nloc[q]);
+        }
       }
     }
-    group_sync<THREADS>();
+    if (!has_n) break;
     it = it_n;
     item = item_n;
   }
@@ -335,7 +406,27 @@ __global__ void __launch_bounds__(160) finalize_kernel(const uint32_t* __restric
   }
 }
 
-struct ClassCfg { int S; int threads; };
+int64_t env_i64(const char* name, int64_t dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoll(v) : dflt;
+}
+
+// Class limits in 64-base blocks: a scaffold of nb blocks is counted with S = 1 if nb <= limit[0], S = 2 if
+// nb <= limit[1], S = 3 if nb <= limit[2], else S = 4 (whole if nb <= limit[3], otherwise in chunks of limit[3]
+// blocks).  The 16-bit counters bound every item to 65 535 super-k-mers: 2 047 / 3 071 / 4 095 blocks for S = 2 / 3 / 4.
+// Env overrides are for tuning runs only and are clamped to those bounds.
+struct Limits { int64_t t[4]; };
+const Limits& limits() {
+  static const Limits L = [] {
+    Limits l;
+    l.t[0] = std::max<int64_t>(0, env_i64("DBB_K1_T1", 32));                                   // <= 2 kb   : S = 1
+    l.t[1] = std::min<int64_t>(2047, std::max(l.t[0], env_i64("DBB_K1_T2", 512)));             // <= 33 kb  : S = 2
+    l.t[2] = std::min<int64_t>(3071, std::max(l.t[1], env_i64("DBB_K1_T3", 1696)));            // <= 108 kb : S = 3
+    l.t[3] = std::min<int64_t>(4095, std::max<int64_t>(l.t[2] + 1, env_i64("DBB_K1_CHUNK", 4032)));   // S = 4 chunk: 258 kb
+    return l;
+  }();
+  return L;
+}
 
 }  // namespace
 
@@ -347,7 +438,6 @@ struct dbb_count_plan {
   uint32_t class_count[4] = {0, 0, 0, 0};
   Item* d_items = nullptr;
   size_t cap_items = 0;
-  uint32_t* d_counters = nullptr;       // [4] (kept for the ABI's memset; the schedule is static)
   uint32_t n_split = 0;
   size_t cap_split = 0;
   uint32_t* d_split_scaffold = nullptr;
@@ -366,7 +456,6 @@ namespace {
 bool g_tables_uploaded[64] = {false};   // per device ordinal (constants live in each device's module image)
 
 int upload_tables() {
-  // per device would be more general; one device per process is the deployment model (one rank per GPU)
   int dev = 0;
   DBB_CUDA_TRY(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64) { dbb::set_error("device ordinal out of range"); return DBB_ERR_UNSUPPORTED; }
@@ -379,31 +468,23 @@ int upload_tables() {
   return DBB_OK;
 }
 
-int64_t env_i64(const char* name, int64_t dflt) {
-  const char* v = getenv(name);
-  return (v && *v) ? atoll(v) : dflt;
-}
-
-template <int S, int THREADS>
+template <int S, int WPI, int MINB>
 int launch_class(const dbb_count_plan* plan, int cls, const void* d_codes, const void* d_valid,
                  uint32_t* d_counts, float* d_freq, int64_t freq_stride, cudaStream_t st) {
   const uint32_t n = plan->class_count[cls];
   if (n == 0) return DBB_OK;
-  constexpr int BINS = 1 << (2 * (3 + S));
-  const size_t smem = (S == 1 ? 256 : 256 + BINS) * sizeof(uint32_t);
-  auto kern = count_kernel<S, THREADS>;
+  const size_t smem = (size_t)(256 + Geo<S>::WORDS + 160 + WPI * 16) * sizeof(uint32_t);
+  auto kern = count_kernel<S, WPI, MINB>;
   DBB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
-  DBB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem));
+  DBB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * WPI, smem));
   if (occ < 1) { dbb::set_error("count kernel S=%d does not fit on the device", S); return DBB_ERR_CUDA; }
-  // DBB_K1_OCC<S> caps the CTAs per SM of a class so that the class kernels share the SMs from the start instead of
-  // overlapping only at their tails (tuning switch; 0 = the occupancy limit)
+  // DBB_K1_OCC<S> caps the CTAs per SM of a class (tuning switch; 0 = the occupancy limit)
   static const int64_t cap = env_i64(S == 1 ? "DBB_K1_OCC1" : S == 2 ? "DBB_K1_OCC2" : S == 3 ? "DBB_K1_OCC3" : "DBB_K1_OCC4", 0);
   if (cap > 0 && cap < occ) occ = (int)cap;
-  uint32_t grid = (uint32_t)std::min<int64_t>((int64_t)occ * plan->sm_count, (int64_t)n);
-  kern<<<grid, THREADS, smem, st>>>(plan->d_items + plan->class_begin[cls], n, plan->d_counters + cls,
-                                    (const uint4*)d_codes, (const uint64_t*)d_valid, d_counts, d_freq,
-                                    freq_stride, plan->d_split_counts);
+  const uint32_t grid = (uint32_t)std::min<int64_t>((int64_t)occ * plan->sm_count, (int64_t)n);
+  kern<<<grid, 32 * WPI, smem, st>>>(plan->d_items + plan->class_begin[cls], n, (const uint4*)d_codes,
+                                       (const uint64_t*)d_valid, d_counts, d_freq, freq_stride, plan->d_split_counts);
   DBB_CUDA_TRY(cudaGetLastError());
   return DBB_OK;
 }
@@ -421,11 +502,8 @@ int count_plan_rebuild(dbb_count_plan* plan, const int64_t* h_blk_off, int64_t n
   plan->total_blocks = n_seq ? h_blk_off[n_seq] : 0;
   if (plan->total_blocks >= (1ll << 32)) { dbb::set_error("batch exceeds 2^32 blocks"); return DBB_ERR_INVALID; }
 
-  // class thresholds in blocks (64 bases); env overrides are for tuning runs only
-  static const int64_t t1 = env_i64("DBB_K1_T1", 128);         // <= 8 kb    : S = 1, one warp per scaffold
-  static const int64_t t2 = env_i64("DBB_K1_T2", 512);         // <= 33 kb   : S = 2
-  static const int64_t t3 = env_i64("DBB_K1_T3", 4300);        // <= 275 kb  : S = 3
-  static const int64_t chunk = env_i64("DBB_K1_CHUNK", 16384); // S = 4 chunk: 1 Mb
+  const Limits& lim = limits();
+  const int64_t t1 = lim.t[0], t2 = lim.t[1], t3 = lim.t[2], chunk = lim.t[3];
   std::vector<Item> cls[4];
   plan->h_split.clear();
   for (int64_t s = 0; s < n_seq; ++s) {
@@ -486,6 +564,12 @@ int count_plan_rebuild(dbb_count_plan* plan, const int64_t* h_blk_off, int64_t n
 
 }  // namespace dbb
 
+DBB_EXPORT int dbb_count_class_limits(int64_t* limits4) {
+  DBB_REQUIRE(limits4 != nullptr, "NULL argument");
+  for (int i = 0; i < 4; ++i) limits4[i] = limits().t[i];
+  return DBB_OK;
+}
+
 DBB_EXPORT int dbb_count_plan_create(const int64_t* h_blk_off, int64_t n_seq, dbb_count_plan** out) {
   DBB_REQUIRE(out != nullptr, "bad arguments");
   *out = nullptr;
@@ -495,8 +579,7 @@ DBB_EXPORT int dbb_count_plan_create(const int64_t* h_blk_off, int64_t n_seq, db
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&plan->sm_count, cudaDevAttrMultiProcessorCount, dev);
-  cudaError_t e = cudaMalloc(&plan->d_counters, 4 * sizeof(uint32_t));
-  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&plan->ev_fork, cudaEventDisableTiming);
+  cudaError_t e = cudaEventCreateWithFlags(&plan->ev_fork, cudaEventDisableTiming);
   for (int c = 0; c < 4 && e == cudaSuccess; ++c) {
     e = cudaStreamCreateWithFlags(&plan->class_stream[c], cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&plan->ev_join[c], cudaEventDisableTiming);
@@ -516,7 +599,6 @@ DBB_EXPORT int dbb_count_plan_create(const int64_t* h_blk_off, int64_t n_seq, db
 DBB_EXPORT int dbb_count_plan_destroy(dbb_count_plan* plan) {
   if (!plan) return DBB_OK;
   cudaFree(plan->d_items);
-  cudaFree(plan->d_counters);
   cudaFree(plan->d_split_scaffold);
   cudaFree(plan->d_split_counts);
   for (int c = 0; c < 4; ++c) {
@@ -539,25 +621,24 @@ DBB_EXPORT int dbb_tetra_count_dev(dbb_count_plan* plan, const void* d_codes, co
   DBB_REQUIRE(!d_freq || freq_stride >= DBB_NUM_KMERS, "freq_stride < 136");
   if (!d_freq) freq_stride = DBB_NUM_KMERS;
   cudaStream_t st = (cudaStream_t)stream;
-  DBB_CUDA_TRY(cudaMemsetAsync(plan->d_counters, 0, 4 * sizeof(uint32_t), st));
   if (plan->n_split)
     DBB_CUDA_TRY(cudaMemsetAsync(plan->d_split_counts, 0, (size_t)plan->n_split * DBB_NUM_KMERS * sizeof(uint32_t), st));
-  // fork: every class kernel on its own stream behind the memsets, join back into the caller's stream
+  // fork: every class kernel on its own stream behind the memset, join back into the caller's stream
   DBB_CUDA_TRY(cudaEventRecord(plan->ev_fork, st));
   int rc = DBB_OK;
   for (int c = 3; c >= 0 && rc == DBB_OK; --c) {            // longest-running class first
     if (plan->class_count[c] == 0) continue;
     cudaStream_t cs = plan->class_stream[c];
     DBB_CUDA_TRY(cudaStreamWaitEvent(cs, plan->ev_fork, 0));
-    // CTA sizes: env overrides exist for tuning sweeps (profiles/), the defaults are the measured best
-    static const int thr4 = (int)env_i64("DBB_K1_THR4", 512), thr3 = (int)env_i64("DBB_K1_THR3", 256),
-                     thr2 = (int)env_i64("DBB_K1_THR2", 64);
-#define DBB_LAUNCH(S_, T_) rc = launch_class<S_, T_>(plan, c, d_codes, d_valid, d_counts, d_freq, freq_stride, cs)
+    // warps per item (= per CTA) and ring depth: env overrides exist for tuning sweeps (profiles/), the defaults are
+    // the measured best
+    static const int w2 = (int)env_i64("DBB_K1_WPI2", 2), w3 = (int)env_i64("DBB_K1_WPI3", 2), w4 = (int)env_i64("DBB_K1_WPI4", 8);
+#define DBB_LAUNCH(S_, W_, B_) rc = launch_class<S_, W_, B_>(plan, c, d_codes, d_valid, d_counts, d_freq, freq_stride, cs)
     switch (c) {
-      case 3: if (thr4 >= 1024) DBB_LAUNCH(4, 1024); else DBB_LAUNCH(4, 512); break;
-      case 2: if (thr3 >= 512) DBB_LAUNCH(3, 512); else if (thr3 >= 256) DBB_LAUNCH(3, 256); else if (thr3 >= 128) DBB_LAUNCH(3, 128); else DBB_LAUNCH(3, 64); break;
-      case 1: if (thr2 >= 256) DBB_LAUNCH(2, 256); else if (thr2 >= 128) DBB_LAUNCH(2, 128); else if (thr2 >= 64) DBB_LAUNCH(2, 64); else DBB_LAUNCH(2, 32); break;
-      default: DBB_LAUNCH(1, 32); break;
+      case 3: if (w4 >= 8) DBB_LAUNCH(4, 8, 6); else if (w4 >= 4) DBB_LAUNCH(4, 4, 6); else DBB_LAUNCH(4, 2, 6); break;
+      case 2: if (w3 >= 4) DBB_LAUNCH(3, 4, 8); else if (w3 >= 2) DBB_LAUNCH(3, 2, 12); else DBB_LAUNCH(3, 1, 16); break;
+      case 1: if (w2 >= 2) DBB_LAUNCH(2, 2, 12); else DBB_LAUNCH(2, 1, 16); break;
+      default: DBB_LAUNCH(1, 1, 16); break;
     }
 #undef DBB_LAUNCH
     if (rc != DBB_OK) return rc;

@@ -97,6 +97,10 @@ int dbb_count_plan_create(const int64_t* h_blk_off, int64_t n_seq, dbb_count_pla
 int dbb_count_plan_destroy(dbb_count_plan* plan);
 /* number of kernels one dbb_tetra_count_dev call launches (for launch accounting) */
 int dbb_count_plan_launches(const dbb_count_plan* plan);
+/* The kernel classes of stage 1, in 64-base blocks: a scaffold of nb blocks is counted with super-k-mers of
+ * S = 1 / 2 / 3 windows when nb <= limits4[0] / [1] / [2], else S = 4, whole if nb <= limits4[3] and otherwise in
+ * chunks of limits4[3] blocks (informational: tests straddle these boundaries, results do not depend on them). */
+int dbb_count_class_limits(int64_t* limits4);
 
 /* packed planes -> counts uint32[n_seq][136] (bit-exact) and freq float[n_seq][freq_stride]
  * (freq = count / sum(count); all-zero counts give NaN as genomicSignatures.py:147-148 does;

@@ -139,6 +139,23 @@ int main() {
     ROW(4, 1, "u16x2 low-bit half", 1024, 1);
     ROW(3, 1, "u16x2 low-bit half", 128, 16);
     ROW(3, 1, "u16x2 low-bit half", 64, 24);
+    // atomics in flight: how many warps does it take to fill the pipe?
+    ROW(3, 0, "u32 +1   (few warps)", 64, 1);
+    ROW(3, 0, "u32 +1   (few warps)", 128, 1);
+    ROW(3, 0, "u32 +1   (few warps)", 256, 1);
+    ROW(3, 0, "u32 +1   (few warps)", 512, 1);
+    ROW(3, 0, "u32 +1   (few warps)", 1024, 1);
+    ROW(3, 2, "u16x2 top (few warps)", 64, 1);
+    ROW(3, 2, "u16x2 top (few warps)", 128, 1);
+    ROW(3, 2, "u16x2 top (few warps)", 256, 1);
+    ROW(3, 2, "u16x2 top (few warps)", 512, 1);
+    ROW(3, 2, "u16x2 top (few warps)", 1024, 1);
+    ROW(4, 2, "u16x2 top (few warps)", 64, 1);
+    ROW(4, 2, "u16x2 top (few warps)", 128, 1);
+    ROW(4, 2, "u16x2 top (few warps)", 256, 1);
+    ROW(4, 2, "u16x2 top (few warps)", 512, 1);
+    ROW(4, 2, "u16x2 top (few warps)", 32, 6);
+    ROW(3, 2, "u16x2 top (few warps)", 32, 24);
 #undef ROW
     cudaFree(d);
   }

@@ -57,11 +57,21 @@ def test_ragged_lengths_exact(gs):
 
 
 def test_every_kernel_class_and_boundaries_exact(gs):
-    """Lengths straddling the S=1/2/3/4 class thresholds (40, 320, 3072 blocks of 64) and the 16384-block
-    split of very long scaffolds, clean and with invalid bases scattered / in runs / at the ends."""
+    """Lengths straddling the live S=1/2/3/4 class limits (read from the library: dbb_count_class_limits, in blocks of
+    64 bases) by one base either side, and the chunking of very long scaffolds (one chunk, chunk + 1 block, two chunks
+    + 1 base, a chunk count that is not a multiple of 3), clean and with invalid bases scattered / in runs / at the ends.
+    A poly-A scaffold as long as one S = 4 chunk puts every super-k-mer of the chunk into ONE 16-bit counter."""
+    import ctypes
+    from dbb_b200 import _lib
+    lim = (ctypes.c_int64 * 4)()
+    _lib.check(_lib.lib().dbb_count_class_limits(lim))
+    t1, t2, t3, chunk = [int(x) for x in lim]
+    assert 0 <= t1 <= t2 <= t3 < chunk <= 4095
     rng = np.random.RandomState(2)
-    lens = [40 * 64 - 1, 40 * 64, 40 * 64 + 1, 3000, 5001, 320 * 64 - 3, 320 * 64, 320 * 64 + 5, 33333,
-            3072 * 64 - 1, 3072 * 64 + 1, 250001, 16384 * 64 + 12345, 2 * 16384 * 64 + 1]
+    lens = []
+    for t in (t1, t2, t3, chunk):
+        lens += [t * 64 - 1, t * 64, t * 64 + 1, t * 64 + 64, t * 64 + 65]
+    lens += [3000, 5001, 33333, 250001, 2 * chunk * 64 + 1, 4 * chunk * 64 + 12345]
     seqs = []
     for L in lens:
         a = util.random_dna(rng, L)
@@ -71,6 +81,9 @@ def test_every_kernel_class_and_boundaries_exact(gs):
         s = rng.randint(0, max(1, L - 600)); b[s:s + rng.randint(10, 500)] |= 0x20
         b[:2] = ord('N'); b[-3:] = ord('n')
         seqs.append(b)
+    seqs.append(np.full(chunk * 64, ord('A'), dtype=np.uint8))
+    seqs.append(np.full(t3 * 64, ord('G'), dtype=np.uint8))
+    seqs.append(np.full(t2 * 64, ord('T'), dtype=np.uint8))
     _check_batch(gs, seqs)
 
 
