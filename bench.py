@@ -408,8 +408,9 @@ def run_ours(args):
             _lib.check(L.dbb_tetra_signatures_host(_lib.ptr(a_np), _lib.ptr(seq_off), my_n, _lib.ptr(h_counts), _lib.ptr(h_freq)))
 
         def e2e_pairs():
-            if world == 1 and args.no_prune:
-                return _pairs.run_pairs_host(h_freq, tables, k=K_NN, topk_filter=topk_filter, want_count=True)
+            if world == 1:
+                # host buffers in, host buffers out: the call TdNeighbours.knn makes
+                return _pairs.run_knn_host(h_freq, tables, k=K_NN, topk_filter=topk_filter, prune=0 if args.no_prune else 1)
             # the host-produced signatures go up (and, N > 1, are gathered through the device), the row block runs,
             # its results are copied back to the host
             f = torch.from_numpy(h_freq).to(dev, non_blocking=True)
@@ -507,10 +508,7 @@ def run_ours(args):
     ms_kernels = ms_knn
     if phase_events:
         # pairs_kernel + merge_kernel launches only (the sweeps), without the planning ops around them
-        per_step = []
-        for marks in phase_events:
-            d = {name: e0.elapsed_time(e1) for (_, e0), (name, e1) in zip(marks, marks[1:])}
-            per_step.append(d)
+        per_step = phase_events                     # one dict of device times per timed step (dbb_knn_output.ms_*)
         ms_plan = sum(d['plan'] for d in per_step) / len(per_step)
         ms_sweep = sum(d['sweep'] for d in per_step) / len(per_step)
         ms_second = sum(d['second sweep + merge'] for d in per_step) / len(per_step)
@@ -544,7 +542,7 @@ def run_ours(args):
                 'pipeline_gbp_per_s': total_bp / e2e_s / 1e9, 'pipeline_pairs_per_s': pairs_total / e2e_s,
                 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                 'api': 'dbb_tetra_signatures_host + dbb_pairs_host (pinned host buffers)' if args.no_prune else
-                       'dbb_tetra_signatures_host (pinned host buffers) + H2D of the signatures, device.pairs_pruned, D2H of the results'},
+                       'dbb_tetra_signatures_host + dbb_knn_host (pinned host buffers)' if world == 1 else 'dbb_tetra_signatures_host (pinned host buffers) + H2D of the signatures, all-gather, dbb_knn_dev, D2H of the results'},
         'pruning': pruning,
         'gpu_launches': launches_per_step * args.steps, 'launches_per_step': launches_per_step,
         'clocks': clocks, 'verified_vs_oracle': verified, 'oracle_check_stage2': oracle_check,

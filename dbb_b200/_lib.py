@@ -66,6 +66,18 @@ class PruneBuffers(ctypes.Structure):
                 ('info', c_vp), ('scratch', c_vp), ('scratch_bytes', c_i64)]
 
 
+class KnnParams(ctypes.Structure):
+    _fields_ = [('k', c_i32), ('topk_filter', c_i32), ('prune', c_i32), ('n_classes', c_i32), ('margin', ctypes.c_float),
+                ('rank', c_i32), ('world', c_i32)]
+
+
+class KnnOutput(ctypes.Structure):
+    _fields_ = [('cap_rows', c_i64), ('row_ids', c_vp), ('knn_idx', c_vp), ('knn_dist', c_vp), ('count', c_vp),
+                ('neighbour_bp', c_vp), ('n_rows', c_i64), ('tiles_visited', c_i64), ('tiles_total', c_i64),
+                ('pruned', c_i32), ('launches', c_i32), ('ms_plan', ctypes.c_float), ('ms_sweep', ctypes.c_float),
+                ('ms_second', ctypes.c_float)]
+
+
 class MergeInput(ctypes.Structure):
     _fields_ = [('search', RefineInput), ('own', c_vp)]
 
@@ -83,6 +95,8 @@ SIGNATURES = {
     'dbb_last_error': (ctypes.c_char_p, []),
     'dbb_version': (ctypes.c_int, []),
     'dbb_device_info': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'dbb_ctx_create': (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(c_vp)]),
+    'dbb_ctx_destroy': (ctypes.c_int, [c_vp]),
     'dbb_kmer_lut': (ctypes.c_int, [c_vp]),
     'dbb_kmer_names': (ctypes.c_int, [c_vp]),
     'dbb_packed_blocks': (c_i64, [c_i64]),
@@ -105,6 +119,8 @@ SIGNATURES = {
     'dbb_prune_plan_dev': (ctypes.c_int, [ctypes.POINTER(PruneInput), ctypes.POINTER(PruneBuffers), c_vp]),
     'dbb_prune_second_dev': (ctypes.c_int, [ctypes.POINTER(PruneInput), ctypes.POINTER(PruneBuffers), c_vp, c_i64, c_vp]),
     'dbb_prune_merge_dev': (ctypes.c_int, [ctypes.POINTER(PruneBuffers), c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'dbb_knn_dev': (ctypes.c_int, [c_vp, ctypes.POINTER(PairsInput), ctypes.POINTER(KnnParams), ctypes.POINTER(KnnOutput), c_vp]),
+    'dbb_knn_host': (ctypes.c_int, [c_vp, ctypes.POINTER(PairsInput), ctypes.POINTER(KnnParams), ctypes.POINTER(KnnOutput)]),
     'dbb_refine_dev': (ctypes.c_int, [ctypes.POINTER(RefineInput), ctypes.POINTER(RefineOutput), c_vp]),
     'dbb_refine_host': (ctypes.c_int, [ctypes.POINTER(RefineInput), ctypes.POINTER(RefineOutput)]),
     'dbb_merge_table_dev': (ctypes.c_int, [ctypes.POINTER(MergeInput), c_vp, c_vp, c_vp]),

@@ -114,6 +114,48 @@ def run_pairs_host(sig, tables, k=0, topk_filter=0, want_count=False, want_td_ma
     return res
 
 
+def run_knn_host(sig, tables, k=20, topk_filter=0, prune=-1, n_classes=8, margin=1e-5, rank=0, world=1, ctx=None):
+    """``dbb_knn_host``: sig float[N,136] and the PairTables on the host -> dict of numpy outputs (idx, dist, count,
+    neighbour_bp, row_ids, plus the statistics of the call).  prune: 1 tile-skipping sweep, 0 full sweep, -1 auto."""
+    L = _lib.lib()
+    sig32 = np.ascontiguousarray(sig, dtype=np.float32)
+    n = tables.n
+    if sig32.shape != (n, _lib.NUM_KMERS):
+        raise ValueError('sig must be [N,136]')
+    if not 1 <= k <= _lib.MAX_K:
+        raise ValueError('k must be in 1..%d' % _lib.MAX_K)
+    inp = _lib.PairsInput()
+    inp.n = n
+    inp.sig, inp.length, inp.td_bound = _vp(sig32), _vp(tables.length), _vp(tables.td_bound)
+    inp.metric = _lib.METRICS['l1']
+    if tables.gc is not None:
+        inp.gc, inp.gc_mbin, inp.gc_lbin = _vp(tables.gc), _vp(tables.gc_mbin), _vp(tables.gc_lbin)
+        inp.gc_lo, inp.gc_hi = _vp(tables.gc_lo), _vp(tables.gc_hi)
+        inp.gc_nm, inp.gc_nl = tables.gc_lo.shape
+    if tables.cov is not None:
+        inp.cov, inp.cov_lbin = _vp(tables.cov), _vp(tables.cov_lbin)
+        inp.cov_lo, inp.cov_hi = _vp(tables.cov_lo), _vp(tables.cov_hi)
+        inp.cov_nl = tables.cov_lo.shape[0]
+    n_rt = (n + 127) // 128
+    cap = max(1, n if (world <= 1 or not prune) else min(n, 128 * len(range(rank, n_rt, world))))
+    par = _lib.KnnParams(k, topk_filter, prune, n_classes, float(margin), rank, world)
+    res = {'idx': np.empty((cap, k), dtype=np.int32), 'dist': np.empty((cap, k), dtype=np.float32),
+           'count': np.empty(cap, dtype=np.int32), 'neighbour_bp': np.empty(cap, dtype=np.int64),
+           'row_ids': np.empty(cap, dtype=np.int64)}
+    out = _lib.KnnOutput()
+    out.cap_rows = cap
+    out.row_ids, out.knn_idx, out.knn_dist = _vp(res['row_ids']), _vp(res['idx']), _vp(res['dist'])
+    out.count, out.neighbour_bp = _vp(res['count']), _vp(res['neighbour_bp'])
+    if n:
+        _lib.check(L.dbb_knn_host(ctx, ctypes.byref(inp), ctypes.byref(par), ctypes.byref(out)))
+    rows = int(out.n_rows)
+    for key in list(res):
+        res[key] = res[key][:rows]
+    res.update(tiles_visited=int(out.tiles_visited), tiles_total=int(out.tiles_total), pruned=bool(out.pruned),
+               launches=int(out.launches), ms_plan=float(out.ms_plan), ms_sweep=float(out.ms_sweep), ms_second=float(out.ms_second))
+    return res
+
+
 def objects_to_arrays(seqs):
     """The reference passes a list of objects with .tetraSig/.length/.GC/.coverage (greedy.py:133-141)."""
     n = len(seqs)

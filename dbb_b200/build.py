@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OBJ = os.path.join(CSRC, '_obj')
 LIB = os.path.join(HERE, 'libdbbcuda.so')
-SOURCES = ['table.cu', 'pack.cu', 'count.cu', 'pairs.cu', 'refine.cu', 'prune.cu', 'greedy.cu', 'pca.cu', 'split.cu', 'synth.cu', 'host_api.cu']
+SOURCES = ['table.cu', 'pack.cu', 'count.cu', 'pairs.cu', 'refine.cu', 'prune.cu', 'knn.cu', 'greedy.cu', 'pca.cu', 'split.cu', 'synth.cu', 'host_api.cu']
 HEADERS = [os.path.join(CSRC, 'common.cuh'), os.path.join(HERE, '..', 'include', 'dbb_cuda.h')]
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',

@@ -24,6 +24,41 @@ const KmerTable& kmer_table();
 // internal: rebuild a count plan in place (count.cu), used by the host-buffer entry points
 int count_plan_rebuild(dbb_count_plan* plan, const int64_t* h_blk_off, int64_t n_seq, cudaStream_t st);
 
+// grow-only device buffer owned by a context (no destructor: a context is freed explicitly by dbb_ctx_destroy, the
+// per-device default contexts live until the process ends and are never torn down behind the CUDA runtime's back)
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes);
+  void release();
+};
+
+// per-context state of the host entry points, defined where it is used
+struct SigState;         // host_api.cu : dbb_tetra_signatures_host
+struct PairsHostState;   // host_api.cu : dbb_pairs_host
+struct KnnState;         // knn.cu      : dbb_knn_dev / dbb_knn_host
+void free_sig_state(SigState*);
+void free_pairs_state(PairsHostState*);
+void free_knn_state(KnnState*);
+
+}  // namespace dbb
+
+// One context = one device: its stream, device scratch and cached plans.  The host entry points without a context
+// argument use the default context of the CURRENT device (created on first use), so a process that switches devices
+// between calls never launches on another device's stream or buffers.
+struct dbb_ctx {
+  int device = 0;
+  cudaStream_t st = nullptr;
+  dbb::SigState* sig = nullptr;
+  dbb::PairsHostState* pairs = nullptr;
+  dbb::KnnState* knn = nullptr;
+  void* mu = nullptr;            // std::mutex*: one host-buffer call at a time per context
+};
+
+namespace dbb {
+// NULL -> the default context of the current device; otherwise `given`, which must belong to the current device
+int ctx_resolve(dbb_ctx* given, dbb_ctx** out);
+struct CtxLock { explicit CtxLock(dbb_ctx* c); ~CtxLock(); void* m; };
 }  // namespace dbb
 
 #define DBB_CUDA_TRY(expr)                                                                     \

@@ -1,36 +1,131 @@
 // Host-buffer entry points: the calls a non-CUDA consumer (the reference's Python modules through
-// ctypes) binds.  They own their device scratch, stream the input through the
-// GPU in bounded batches and return with the results in the caller's buffers.
+// ctypes) binds.  They own their device scratch (inside a dbb_ctx, one per device), stream
+// the input through the GPU in bounded batches and return with the results in the caller's buffers.
 #include "common.cuh"
 #include <algorithm>
 #include <cstdlib>
 #include <mutex>
 #include <vector>
 
-namespace {
+namespace dbb {
 
-struct DevBuf {
-  void* p = nullptr;
-  size_t cap = 0;
-  int reserve(size_t bytes) {
-    if (bytes <= cap) return DBB_OK;
-    if (p) cudaFree(p);
-    p = nullptr; cap = 0;
-    cudaError_t e = cudaMalloc(&p, bytes);
-    if (e != cudaSuccess) { dbb::set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); return DBB_ERR_NOMEM; }
-    cap = bytes;
-    return DBB_OK;
-  }
-  ~DevBuf() { if (p) cudaFree(p); }
-};
+int DevBuf::reserve(size_t bytes) {
+  if (bytes <= cap) return DBB_OK;
+  if (p) cudaFree(p);
+  p = nullptr; cap = 0;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) { set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); return DBB_ERR_NOMEM; }
+  cap = bytes;
+  return DBB_OK;
+}
+void DevBuf::release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 
-struct Lane {            // one in-flight batch
+struct Lane {            // one in-flight batch of stage 1
   cudaStream_t st = nullptr;
   DevBuf ascii, seq_off, blk_off, codes, valid, counts, freq;
   dbb_count_plan* plan = nullptr;
   int64_t s0 = 0, s1 = 0;
   std::vector<int64_t> h_off, h_blk;
 };
+struct SigState { Lane lanes[2]; };
+struct PairsHostState {
+  DevBuf dense, sig, len, tdb, gc, gcm, gcl, gclo, gchi, cov, covl, covlo, covhi;
+  DevBuf o_idx, o_dist, o_cnt, o_bp, o_td, o_gc, o_cov;
+};
+
+void free_sig_state(SigState* s) {
+  if (!s) return;
+  for (auto& L : s->lanes) {
+    for (DevBuf* b : {&L.ascii, &L.seq_off, &L.blk_off, &L.codes, &L.valid, &L.counts, &L.freq}) b->release();
+    if (L.plan) dbb_count_plan_destroy(L.plan);
+    if (L.st) cudaStreamDestroy(L.st);
+  }
+  delete s;
+}
+void free_pairs_state(PairsHostState* s) {
+  if (!s) return;
+  for (DevBuf* b : {&s->dense, &s->sig, &s->len, &s->tdb, &s->gc, &s->gcm, &s->gcl, &s->gclo, &s->gchi, &s->cov, &s->covl, &s->covlo,
+                    &s->covhi, &s->o_idx, &s->o_dist, &s->o_cnt, &s->o_bp, &s->o_td, &s->o_gc, &s->o_cov}) b->release();
+  delete s;
+}
+
+CtxLock::CtxLock(dbb_ctx* c) : m(c->mu) { static_cast<std::mutex*>(m)->lock(); }
+CtxLock::~CtxLock() { static_cast<std::mutex*>(m)->unlock(); }
+
+static int make_ctx(int device, dbb_ctx** out) {
+  dbb_ctx* c = new dbb_ctx();
+  c->device = device;
+  c->mu = new std::mutex();
+  cudaError_t e = cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    set_error("cudaStreamCreate failed: %s", cudaGetErrorString(e));
+    delete static_cast<std::mutex*>(c->mu); delete c;
+    return DBB_ERR_CUDA;
+  }
+  *out = c;
+  return DBB_OK;
+}
+
+int ctx_resolve(dbb_ctx* given, dbb_ctx** out) {
+  int dev = 0;
+  DBB_CUDA_TRY(cudaGetDevice(&dev));
+  if (given) {
+    if (given->device != dev) {
+      set_error("invalid argument: the context belongs to device %d, the current device is %d", given->device, dev);
+      return DBB_ERR_INVALID;
+    }
+    *out = given;
+    return DBB_OK;
+  }
+  if (dev < 0 || dev >= 64) { set_error("device ordinal out of range"); return DBB_ERR_UNSUPPORTED; }
+  static std::mutex g_mu;
+  static dbb_ctx* g_default[64] = {nullptr};       // never destroyed: no cudaFree after the runtime is torn down
+  std::lock_guard<std::mutex> lock(g_mu);
+  if (!g_default[dev]) {
+    int rc = make_ctx(dev, &g_default[dev]);
+    if (rc != DBB_OK) return rc;
+  }
+  *out = g_default[dev];
+  return DBB_OK;
+}
+
+}  // namespace dbb
+
+DBB_EXPORT int dbb_ctx_create(int device, dbb_ctx** ctx) {
+  DBB_REQUIRE(ctx != nullptr, "NULL argument");
+  *ctx = nullptr;
+  int cur = 0;
+  DBB_CUDA_TRY(cudaGetDevice(&cur));
+  if (device < 0) device = cur;
+  int n_dev = 0;
+  DBB_CUDA_TRY(cudaGetDeviceCount(&n_dev));
+  DBB_REQUIRE(device < n_dev, "no such device");
+  if (device != cur) DBB_CUDA_TRY(cudaSetDevice(device));
+  int rc = dbb::make_ctx(device, ctx);
+  if (device != cur) cudaSetDevice(cur);
+  return rc;
+}
+
+DBB_EXPORT int dbb_ctx_destroy(dbb_ctx* ctx) {
+  if (!ctx) return DBB_OK;
+  int cur = 0;
+  cudaGetDevice(&cur);
+  if (cur != ctx->device) cudaSetDevice(ctx->device);
+  if (ctx->st) cudaStreamSynchronize(ctx->st);
+  dbb::free_sig_state(ctx->sig);
+  dbb::free_pairs_state(ctx->pairs);
+  dbb::free_knn_state(ctx->knn);
+  if (ctx->st) cudaStreamDestroy(ctx->st);
+  if (cur != ctx->device) cudaSetDevice(cur);
+  delete static_cast<std::mutex*>(ctx->mu);
+  delete ctx;
+  return DBB_OK;
+}
+
+namespace {
+
+using dbb::DevBuf;
+using dbb::Lane;
 
 #define DBB_TRY(expr) do { int _rc = (expr); if (_rc != DBB_OK) return _rc; } while (0)
 
@@ -88,15 +183,18 @@ DBB_EXPORT int dbb_tetra_signatures_host(const uint8_t* ascii, const int64_t* se
   for (int64_t s = 0; s < n_seq; ++s) DBB_REQUIRE(seq_off[s + 1] >= seq_off[s], "seq_off must be non-decreasing");
 
   // batches of ~batch_bytes of sequence, two in flight (copy of batch b+1 overlaps compute of batch b).  The
-  // lanes (streams, device buffers, count plans) live for the whole process and only grow: a per-sequence caller
-  // such as GenomicSignatures.seqSignature pays no allocation after its first call.
-  static std::mutex mu;
-  static Lane lanes[2];
-  std::lock_guard<std::mutex> lock(mu);
+  // lanes (streams, device buffers, count plans) belong to the default context of the current device and only grow:
+  // a per-sequence caller such as GenomicSignatures.seqSignature pays no allocation after its first call.
+  dbb_ctx* ctx = nullptr;
+  int rc = dbb::ctx_resolve(nullptr, &ctx);
+  if (rc != DBB_OK) return rc;
+  dbb::CtxLock lock(ctx);
+  if (!ctx->sig) ctx->sig = new dbb::SigState();
+  Lane* lanes = ctx->sig->lanes;
   const char* env = getenv("DBB_HOST_BATCH_MB");
   const int64_t batch_bytes = (env && *env ? atoll(env) : 256) << 20;
-  int rc = DBB_OK;
-  for (auto& L : lanes) {
+  for (int i = 0; i < 2; ++i) {
+    Lane& L = lanes[i];
     if (L.st) continue;
     cudaError_t e = cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking);
     if (e != cudaSuccess) { dbb::set_error("cudaStreamCreate failed: %s", cudaGetErrorString(e)); L.st = nullptr; return DBB_ERR_CUDA; }
@@ -144,13 +242,17 @@ DBB_EXPORT int dbb_pairs_host(const dbb_pairs_input* in, int64_t row0, int64_t r
   if (row1 == row0 || in->n == 0) return DBB_OK;
   DBB_REQUIRE(in->sig && in->length, "sig/length are required");
   const size_t n = (size_t)in->n, rows = (size_t)(row1 - row0);
-  // process-lifetime scratch (grow-only), one host-buffer call at a time
-  static std::mutex mu;
-  static cudaStream_t st = nullptr;
-  static DevBuf dense, sig, len, tdb, gc, gcm, gcl, gclo, gchi, cov, covl, covlo, covhi;
-  static DevBuf o_idx, o_dist, o_cnt, o_bp, o_td, o_gc, o_cov;
-  std::lock_guard<std::mutex> lock(mu);
-  if (!st) DBB_CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  // scratch of the current device's default context (grow-only), one host-buffer call at a time
+  dbb_ctx* ctx = nullptr;
+  int rc0 = dbb::ctx_resolve(nullptr, &ctx);
+  if (rc0 != DBB_OK) return rc0;
+  dbb::CtxLock lock(ctx);
+  if (!ctx->pairs) ctx->pairs = new dbb::PairsHostState();
+  dbb::PairsHostState& B = *ctx->pairs;
+  DevBuf &dense = B.dense, &sig = B.sig, &len = B.len, &tdb = B.tdb, &gc = B.gc, &gcm = B.gcm, &gcl = B.gcl, &gclo = B.gclo, &gchi = B.gchi,
+         &cov = B.cov, &covl = B.covl, &covlo = B.covlo, &covhi = B.covhi;
+  DevBuf &o_idx = B.o_idx, &o_dist = B.o_dist, &o_cnt = B.o_cnt, &o_bp = B.o_bp, &o_td = B.o_td, &o_gc = B.o_gc, &o_cov = B.o_cov;
+  cudaStream_t st = ctx->st;
   int rc = DBB_OK;
   dbb_pairs_input d = *in;
   dbb_pairs_output o = *out;

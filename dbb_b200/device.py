@@ -186,209 +186,77 @@ def pairs(sig_padded, dt, row0=0, row1=None, k=0, topk_filter=0, want_count=True
     return res
 
 
-_GC_WEIGHTS = None
-_ITEMS_TARGET = int(__import__('os').environ.get('DBB_PRUNE_ITEMS', '740'))    # work items per sweep (~5 per SM; C2: 2 segments per row tile 12.3 ms, 1: 17.8, 4: 13.4)
-
-
-def projection_weights(device):
-    """float32[140]: per canonical tetramer 0 / 0.5 / 1 for <= 1 / 2 / >= 3 G or C, zero for the padding columns.
-    Any weights in [0, 1] give the bound used by pairs_pruned; these spread metagenomes by their GC content, and the
-    saturated form keeps more of the distance than the plain GC fraction (0, .25, .5, .75, 1): on the synthetic C2 / C4
-    inputs the pair-level bound leaves 29 % / 33 % of the pairs instead of 40 % / 44 %."""
-    global _GC_WEIGHTS
-    if _GC_WEIGHTS is None:
-        names, _ = _lib.kmer_table()
-        w = np.zeros(_lib.SIG_STRIDE, dtype=np.float32)
-        w[:_lib.NUM_KMERS] = [min(1.0, max(0.0, (sum(ch in 'GC' for ch in nm) - 1) / 2.0)) for nm in names]
-        _GC_WEIGHTS = {None: w}
-    key = str(device)
-    if key not in _GC_WEIGHTS:                                         # uploaded once per device
-        _GC_WEIGHTS[key] = torch.from_numpy(_GC_WEIGHTS[None]).to(device)
-    return _GC_WEIGHTS[key]
-
-
-class _SortedTables(object):
-    pass
-
-
-def pairs_pruned(sig_padded, dt, row0=0, row1=None, k=0, topk_filter=0, want_count=True, metric='l1', margin=1e-5,
-                 n_classes=8, timings=None, part=None):
-    """Same results as ``pairs`` (no masks), skipping 128 x 128 tiles of the pair matrix that cannot matter.
+def pairs_pruned(sig_padded, dt, k=20, topk_filter=0, want_count=True, metric='l1', margin=1e-5, n_classes=8, timings=None,
+                 part=None, prune=1, ctx=None):
+    """k nearest neighbours + neighbourhood sizes of all rows through ONE C call, ``dbb_knn_dev`` (csrc/knn.cu): same
+    results as ``pairs`` (no masks), skipping 128 x 128 tiles of the pair matrix that cannot matter.
 
     Signatures sum to 1, so for ANY weights w_k in [0, 1] and p = sum_k w_k sig_k:  L1(a, b) >= 2 |p_a - p_b|
-    (sum_k (w_k - 1/2)(a_k - b_k) equals p_a - p_b and is at most L1 / 2 in magnitude).  With the scaffolds sorted by p
-    every tile has a p interval; a tile pair whose intervals are farther apart than half the largest TD bound of its
-    rows and columns holds no TD neighbour (the bound of a pair is the bound of its shorter scaffold), hence nothing
-    that counts and no candidate of a TD-filtered top-k.  For an unfiltered top-k a second launch visits the tiles whose
-    lower bound does not exceed the k-th best distance found so far of some row of the row tile, and the lists are
-    merged; results are identical to the unpruned sweep, ties included (lists are ordered by (distance, original id)).
-    The sort key is (TD-bound class, p): the bound of a pair is the bound of its shorter scaffold, so tiles of long
-    scaffolds (small bounds) only need their near neighbours among each other; ``n_classes`` equal-count classes of the
-    per-scaffold bound keep the tiles homogeneous (any arrangement is exact, the intervals are taken per tile).
-    part=(rank, world): multi-GPU -- the row tiles of the sorted order are dealt to the ranks by decreasing work (their
-    tile lists differ in length by an order of magnitude, contiguous blocks would not balance); the rank's results are
-    returned for its rows only.  Otherwise [row0, row1) are positions in the sorted order.  The dict carries ``row_ids``,
-    the original ids of the returned rows, and ``tiles_visited`` / ``tiles_total``.  Planning (projection, sort, gathers,
-    tile lists, list merge) is csrc/prune.cu (``dbb_prune_plan_dev`` / ``_second_dev`` / ``_merge_dev``), enqueued on the
-    same stream with a single host read (the list sizes); the distance work is the same pairs_kernel."""
+    (sum_k (w_k - 1/2)(a_k - b_k) equals p_a - p_b and is at most L1 / 2 in magnitude).  With the scaffolds sorted by
+    (TD-bound class, p) every tile has a p interval; a tile pair whose intervals are farther apart than half the largest
+    TD bound of its rows and columns holds no TD neighbour (the bound of a pair is the bound of its shorter scaffold),
+    hence nothing that counts and no candidate of a TD-filtered top-k.  For a top-k that is not TD-filtered a second
+    launch visits the tiles whose lower bound does not exceed the k-th best distance found so far of some row of the row
+    tile, and the lists are merged; results are identical to the unpruned sweep, ties included.  The library checks on
+    the device that every finite signature row sums to 1 (the bound's precondition) and refuses the call otherwise
+    (``prune=1``) or runs the full sweep (``prune=-1``).
+    part=(rank, world): multi-GPU -- the row tiles of the sorted order are dealt to the ranks by decreasing work; the
+    rank's rows come back in ascending sorted position.  The dict carries ``row_ids`` (original ids of the returned
+    rows), ``tiles_visited`` / ``tiles_total`` / ``launches`` and the device times of the phases."""
     require_cuda()
     if metric != 'l1':
         raise ValueError('pairs_pruned: the projection bound is for the Manhattan distance')
     if want_count and dt.td_bound is None:
         raise ValueError('pairs_pruned: without a TD bound every pair may count, nothing can be skipped (use pairs)')
     n = dt.n
-    if part is not None:
-        row0, row1 = 0, n
-    row1 = n if row1 is None else row1
     dev = sig_padded.device
-    T = 128
-    marks = []
-
-    def mark(name):
-        if timings is not None:
-            e = torch.cuda.Event(enable_timing=True)
-            e.record()
-            marks.append((name, e))
-
-    mark('start')
-    world = part[1] if part is not None else 1
-    rank = part[0] if part is not None else 0
-    cls = None
-    if dt.td_bound is not None and n_classes > 1:
-        cls = getattr(dt, '_prune_class', None)
-        if cls is None or cls.shape[0] != n or getattr(dt, '_prune_nc', 0) != n_classes:
-            # once per table set (not per sweep): equal-count classes of the per-scaffold TD bound
-            order = torch.empty(n, dtype=torch.int64, device=dev)
-            order[torch.argsort(dt.td_bound, stable=True)] = torch.arange(n, device=dev)
-            cls = ((order * n_classes) // max(n, 1)).to(torch.float32)
-            dt._prune_class, dt._prune_nc = cls, n_classes
-    if len(range(rank, (row1 - row0 + T - 1) // T, world)) == 0:
-        # more ranks than row tiles: nothing for this one
-        res = {'row_ids': torch.empty(0, dtype=torch.int64, device=dev), 'tiles_visited': 0, 'tiles_total': 0, 'launches': 0}
-        if k > 0:
-            res['idx'] = torch.empty((0, k), dtype=torch.int32, device=dev)
-            res['dist'] = torch.empty((0, k), dtype=torch.float32, device=dev)
-        if want_count:
-            res['count'] = torch.empty(0, dtype=torch.int32, device=dev)
-            res['neighbour_bp'] = torch.empty(0, dtype=torch.int64, device=dev)
-        if isinstance(timings, list):
-            for name in ('plan', 'sweep', 'second sweep + merge'):
-                mark(name)
-            timings.append(marks)
-        return res
-    b = _prune_buffers(dt, n, row0, row1, world, dev)
-    st = b.st
-    L = _lib.lib()
-    inp = _lib.PruneInput(n, _p(sig_padded), _p(projection_weights(dev)), _p(cls), _p(dt.length), _p(dt.td_bound), _p(dt.gc),
-                          _p(dt.gc_mbin), _p(dt.gc_lbin), _p(dt.cov), _p(dt.cov_lbin), row0, row1, rank, world, float(margin))
-    _lib.check(L.dbb_prune_plan_dev(ctypes.byref(inp), ctypes.byref(b.struct), _stream()))
-    n_rt, n_ct = b.n_rt, b.n_ct
-    n_mine = len(range(rank, n_rt, world))
-
-    def split_for(n_act, target):
-        # ~5 work items per SM: the lists differ in length by an order of magnitude, whole row tiles do not balance,
-        # but every extra segment refills its own top-k lists
-        return int(min(8, max(1, -(-target // max(n_act, 1)))))
-
-    sp = (b.col_id, b.order, b.off, b.tl, split_for(n_mine, _ITEMS_TARGET), 0 if part is None else n_mine)
-    mark('plan')
-    res = pairs(b.sig, st, row0, row1, k=k, topk_filter=topk_filter, want_count=want_count, metric=metric, sparse=sp)
-    mark('sweep')
-    launches = (10 if world > 1 else 9) + 2                       # planner kernels + pairs_kernel + merge_kernel
-    second = k > 0 and not (topk_filter & FILTER_TD)
-    if second:
-        # unfiltered (or GC / coverage filtered) top-k: candidates may sit beyond the TD window.  Only the affected row
-        # tiles run again (they sort first: the others have empty lists); their rows' lists are merged with the first
-        # sweep's in the (distance, id) order
-        kth = res['dist'][:, k - 1]
-        _lib.check(L.dbb_prune_second_dev(ctypes.byref(inp), ctypes.byref(b.struct), _p(kth), k, _stream()))
-        launches += 6
-    info = b.info.cpu().tolist()                                   # the one host read: list sizes of both plans
-    if info[4]:
-        raise _lib.DbbError('pairs_pruned: %d signature rows do not sum to 1 within %g: the tile-skipping bound '
-                            'L1 >= 2|p_a - p_b| does not hold for them (pass frequencies, or use the full sweep device.pairs)'
-                            % (info[4], 0.3 * margin))
-    visited1, visited, n_aff = info[0], info[0], 0
-    if second:
-        visited, n_aff = info[0] + info[2], info[3]
-        if n_aff:
-            sp2 = (b.col_id, b.order, b.off, b.tl, split_for(n_aff, 2 * _ITEMS_TARGET), n_aff)   # few row tiles, short lists: cut finer
-            r2 = pairs(b.sig, st, row0, row1, k=k, topk_filter=topk_filter, want_count=False, metric=metric, sparse=sp2)
-            _lib.check(L.dbb_prune_merge_dev(ctypes.byref(b.struct), row1 - row0, k, _p(res['idx']), _p(res['dist']),
-                                             _p(r2['idx']), _p(r2['dist']), _stream()))
-            launches += 3
-    mark('second sweep + merge')
+    assert sig_padded.shape == (n, _lib.SIG_STRIDE) and sig_padded.is_contiguous() and sig_padded.dtype == torch.float32
+    rank, world = part if part is not None else (0, 1)
+    n_rt = (n + 127) // 128
+    cap = max(1, n if world <= 1 else min(n, 128 * len(range(rank, n_rt, world))))   # (a rank beyond the row tiles gets no rows)
+    inp = _lib.PairsInput()
+    inp.n = n
+    inp.sig, inp.length, inp.td_bound = _p(sig_padded), _p(dt.length), _p(dt.td_bound)
+    inp.metric = _lib.METRICS[metric]
+    if dt.gc is not None:
+        inp.gc, inp.gc_mbin, inp.gc_lbin, inp.gc_lo, inp.gc_hi = _p(dt.gc), _p(dt.gc_mbin), _p(dt.gc_lbin), _p(dt.gc_lo), _p(dt.gc_hi)
+        inp.gc_nm, inp.gc_nl = dt.gc_lo.shape
+    if dt.cov is not None:
+        inp.cov, inp.cov_lbin, inp.cov_lo, inp.cov_hi = _p(dt.cov), _p(dt.cov_lbin), _p(dt.cov_lo), _p(dt.cov_hi)
+        inp.cov_nl = dt.cov_lo.shape[0]
+    par = _lib.KnnParams(k, topk_filter, prune, n_classes, float(margin), rank, world)
+    res = {'idx': torch.empty((cap, k), dtype=torch.int32, device=dev), 'dist': torch.empty((cap, k), dtype=torch.float32, device=dev),
+           'row_ids': torch.empty(cap, dtype=torch.int64, device=dev)}
+    out = _lib.KnnOutput()
+    out.cap_rows = cap
+    out.row_ids, out.knn_idx, out.knn_dist = _p(res['row_ids']), _p(res['idx']), _p(res['dist'])
+    if want_count:
+        res['count'] = torch.empty(cap, dtype=torch.int32, device=dev)
+        res['neighbour_bp'] = torch.empty(cap, dtype=torch.int64, device=dev)
+        out.count, out.neighbour_bp = _p(res['count']), _p(res['neighbour_bp'])
+    if n:
+        _lib.check(_lib.lib().dbb_knn_dev(ctx, ctypes.byref(inp), ctypes.byref(par), ctypes.byref(out), _stream()))
+    rows = int(out.n_rows)
+    for key in list(res):
+        res[key] = res[key][:rows]
+    res['tiles_visited'], res['tiles_total'] = int(out.tiles_visited), int(out.tiles_total)
+    res['launches'], res['pruned'] = int(out.launches), bool(out.pruned)
+    ms = {'plan': float(out.ms_plan), 'sweep': float(out.ms_sweep), 'second sweep + merge': float(out.ms_second)}
     if isinstance(timings, list):
-        timings.append(marks)                      # events only; the caller reads them after its own synchronisation
+        timings.append(ms)
     elif timings is not None:
-        torch.cuda.synchronize()
-        for (_, e0), (name, e1) in zip(marks, marks[1:]):
-            timings[name] = e0.elapsed_time(e1)
-        timings['tiles_first'], timings['tiles_second'] = visited1, visited - visited1
-    if part is None:
-        res['row_ids'] = b.col_id[row0:row1].to(torch.int64)
-    else:
-        rows_mine = (b.mine.nonzero()[:, 0][:, None] * T + torch.arange(T, device=dev)[None, :]).flatten()
-        rows_mine = rows_mine[rows_mine < n]
-        for key_ in ('idx', 'dist', 'count', 'neighbour_bp'):
-            if key_ in res:
-                res[key_] = res[key_][rows_mine]
-        res['row_ids'] = b.col_id[rows_mine].to(torch.int64)
-    res['tiles_visited'], res['tiles_total'] = visited, n_mine * n_ct
-    res['launches'] = launches
+        timings.update(ms)
     return res
 
 
-class _PruneBuffers(object):
-    pass
-
-
-def _prune_buffers(dt, n, row0, row1, world, dev):
-    """Device buffers of the planner (csrc/prune.cu) for one problem shape, kept on the table object between sweeps:
-    the sorted signature matrix and tables, the tile lists and the planner's scratch."""
-    key = (n, row0, row1, world, str(dev))
-    b = getattr(dt, '_prune_buf', None)
-    if b is not None and b.key == key:
-        return b
-    rows = row1 - row0
-    b = _PruneBuffers()
-    b.key = key
-    b.n_ct, b.n_rt = (n + 127) // 128, (rows + 127) // 128
-    n_slots = -(-b.n_rt // world) if world > 1 else b.n_rt
-    b.sig = torch.empty((n, _lib.SIG_STRIDE), dtype=torch.float32, device=dev)
-    st = _SortedTables()
-    st.n = n
-    for name in ('length', 'td_bound', 'gc', 'gc_mbin', 'gc_lbin', 'cov', 'cov_lbin'):
-        a = getattr(dt, name)
-        setattr(st, name, None if a is None else torch.empty_like(a))
-    st.gc_lo, st.gc_hi, st.cov_lo, st.cov_hi = dt.gc_lo, dt.gc_hi, dt.cov_lo, dt.cov_hi
-    b.st = st
-    b.col_id = torch.empty(n, dtype=torch.int32, device=dev)
-    b.p = torch.empty(n, dtype=torch.float32, device=dev)
-    b.order = torch.empty(b.n_rt, dtype=torch.int32, device=dev)
-    b.off = torch.empty(b.n_rt + 1, dtype=torch.int64, device=dev)
-    b.tl = torch.empty(max(n_slots * b.n_ct, 1), dtype=torch.int32, device=dev)
-    b.cnt = torch.empty(b.n_rt, dtype=torch.int32, device=dev)
-    b.mine = torch.zeros(b.n_rt, dtype=torch.uint8, device=dev)
-    b.info = torch.zeros(8, dtype=torch.int64, device=dev)
-    nbytes = int(_lib.lib().dbb_prune_scratch_bytes(n, rows, world))
-    if nbytes < 0:
-        _lib.check(-1)
-    b.scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    b.struct = _lib.PruneBuffers(_p(b.sig), _p(st.length), _p(st.td_bound), _p(st.gc), _p(st.gc_mbin), _p(st.gc_lbin), _p(st.cov),
-                                 _p(st.cov_lbin), _p(b.col_id), _p(b.p), _p(b.order), _p(b.off), _p(b.tl), _p(b.cnt), _p(b.mine),
-                                 _p(b.info), _p(b.scratch), nbytes)
-    dt._prune_buf = b
-    return b
-
-
 def unsort_rows(res, n):
-    """Results of a full-range pairs_pruned call back in the caller's row order."""
+    """Results of a pairs_pruned call scattered to the rows named by ``row_ids`` (single GPU: already the caller's
+    order; multi-GPU: the rank's rows at their original positions of an [n, ...] array)."""
     out = {}
     ids = res['row_ids']
     for key in ('idx', 'dist', 'count', 'neighbour_bp'):
         if key in res:
-            t = torch.empty_like(res[key])
+            t = torch.empty((n,) + tuple(res[key].shape[1:]), dtype=res[key].dtype, device=res[key].device)
             t[ids] = res[key]
             out[key] = t
     return out

@@ -35,40 +35,27 @@ class TdNeighbours(object):
     def knn(self, sig, length, GC=None, cov=None, k=20, tdDist=None, tdDistPer=None, gcDist=None,
             gcDistPer=None, covDist=None, covDistPer=None, topk_filter=None, metric='l1', prune=None):
         """Returns (idx int32[N,k] padded -1, dist float32[N,k] padded +inf, count int32[N],
-        neighbour_bp int64[N]).
+        neighbour_bp int64[N]).  One ctypes call, ``dbb_knn_host`` (include/dbb_cuda.h); no torch.
 
         Top-k candidates of row i: j != i passing the predicates in ``topk_filter`` (default: the GC
         and coverage filters that are enabled), ordered by (distance asc, j asc).  ``count`` /
         ``neighbour_bp``: size / total length of {j : all enabled predicates hold}, j == i included.
         ``metric``: 'l1' is the reference's Manhattan distance (genomicSignatures.py:183-184); 'l2' (Euclidean) is an
         addition for k-NN callers and cannot be combined with the GC / coverage predicates.
-        ``prune``: use the exact tile-skipping sweep (device.pairs_pruned: same results, about twice as fast on
-        metagenome-like inputs; needs a TD bound, the Manhattan metric and torch for the device plumbing).  Default:
-        whenever those conditions hold; False forces the plain full sweep through the C ABI's host entry point."""
+        ``prune``: the exact tile-skipping sweep (same results, about twice as fast on metagenome-like inputs).  It needs a
+        TD bound, the Manhattan metric and signature rows that sum to 1 -- frequencies do, raw counts do not; the library
+        checks this on the device.  None (default): pruned whenever those conditions hold, otherwise the full sweep on the
+        GPU; True: required (ValueError / DbbError when a condition fails); False: always the full sweep."""
         tables = PairTables(length, GC=GC, coverage=cov, tdDist=tdDist, tdDistPer=tdDistPer, gcDist=gcDist,
                             gcDistPer=gcDistPer, covDist=covDist, covDistPer=covDistPer,
                             fixedSeqLen=self.fixedSeqLen)
         if topk_filter is None:
             topk_filter = (_pairs.FILTER_GC if gcDist is not None else 0) | (_pairs.FILTER_COV if covDist is not None else 0)
         can_prune = tdDist is not None and metric == 'l1' and k > 0 and tables.n > 256
-        if prune is None:
-            prune = can_prune and _torch_cuda()
-        if prune:
-            if not can_prune:
-                raise ValueError('prune=True needs tdDist, the Manhattan metric, k > 0 and more than two tiles of scaffolds')
-            import torch
-            from . import device
-            sig32 = torch.from_numpy(np.ascontiguousarray(sig, dtype=np.float32)).cuda()
-            r = device.unsort_rows(device.pairs_pruned(device.pad_signatures(sig32), device.DevicePairTables(tables), k=k,
-                                                       topk_filter=topk_filter, want_count=True), tables.n)
-            return (r['idx'].cpu().numpy(), r['dist'].cpu().numpy(), r['count'].cpu().numpy(), r['neighbour_bp'].cpu().numpy())
-        res = _pairs.run_pairs_host(sig, tables, k=k, topk_filter=topk_filter, want_count=True, metric=metric)
+        if prune and not can_prune:
+            raise ValueError('prune=True needs tdDist, the Manhattan metric, k > 0 and more than two tiles of scaffolds')
+        if k == 0 or metric != 'l1':
+            res = _pairs.run_pairs_host(sig, tables, k=k, topk_filter=topk_filter, want_count=True, metric=metric)
+            return res['idx'], res['dist'], res['count'], res['neighbour_bp']
+        res = _pairs.run_knn_host(sig, tables, k=k, topk_filter=topk_filter, prune=(-1 if prune is None else int(bool(prune))))
         return res['idx'], res['dist'], res['count'], res['neighbour_bp']
-
-
-def _torch_cuda():
-    try:
-        import torch
-        return torch.cuda.is_available()
-    except ImportError:
-        return False

@@ -52,6 +52,15 @@ int dbb_version(void);
 /* device facts for roofline arithmetic: SM count, compute capability, free/total bytes */
 int dbb_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* free_bytes, int64_t* total_bytes);
 
+/* ---- contexts (SURVEY.md section 8b "Ownership"): a context owns the stream, the device scratch and the cached
+ * plans of ONE device.  Every entry point that takes a dbb_ctx* accepts NULL = the default context of the current
+ * device (created on first use, alive until the process ends); the *_host entry points without a context argument
+ * use that default context too.  A context must be used with its own device current (else DBB_ERR_INVALID) and by one
+ * thread at a time.  device < 0 = the current device. */
+typedef struct dbb_ctx dbb_ctx;
+int dbb_ctx_create(int device, dbb_ctx** ctx);
+int dbb_ctx_destroy(dbb_ctx* ctx);
+
 /* ---- canonical tetramer table: genomicSignatures.py:35-84 (__init__, __makeKmerColNames,
  * ---- __lexicographicallyLowest, __revComp) ------------------------------------------------------ */
 /* lut256[code] = canonical column of the 4-mer with 2-bit code `code` (first base most significant) */
@@ -242,6 +251,45 @@ int dbb_prune_second_dev(const dbb_prune_input* in, const dbb_prune_buffers* buf
  * (distance, id) order of dbb_pairs_output ([rows][k] each, ids as written by dbb_pairs_dev, -1 padding). */
 int dbb_prune_merge_dev(const dbb_prune_buffers* buf, int64_t rows, int32_t k, int32_t* d_idx1, float* d_dist1,
                         const int32_t* d_idx2, const float* d_dist2, void* stream);
+
+/* ---- k nearest neighbours + neighbourhood sizes of all rows in ONE call: the default stage 2 -----------------
+ * (tdNeighbours.py:41-51 with gcNeighbours.py:43-52 / coverageNeighbours.py:41-50 as dbb_pairs_input describes them;
+ * the top-k is the new output of dbb_pairs_output.)  With prune != 0 the library plans and runs the exact
+ * tile-skipping sweep itself -- class quantiles of td_bound, dbb_prune_plan_dev, sparse dbb_pairs_dev, for a top-k that
+ * is not TD-filtered the second plan + sweep + list merge -- and returns the rows in the caller's order; results are
+ * identical to the full sweep (prune == 0), ties included.  prune needs td_bound, the Manhattan metric and signature
+ * rows that sum to 1: rows that do not are counted on the device and the call fails with DBB_ERR_INVALID (prune == 1)
+ * or falls back to the full sweep on the GPU (prune == -1, "auto").
+ * Multi-GPU (world > 1): this rank takes its share of the 128-row tiles of the sorted order, dealt by decreasing work
+ * (prune) or the equal row block [n*rank/world, n*(rank+1)/world) (full sweep); the rows come back in ascending
+ * sorted position with their original ids in row_ids.  The call synchronises `stream` once (list sizes). */
+typedef struct {
+  int32_t k;                   /* 1..DBB_MAX_K */
+  int32_t topk_filter;         /* as dbb_pairs_output.topk_filter */
+  int32_t prune;               /* 1: tile-skipping sweep, 0: full sweep, -1: auto */
+  int32_t n_classes;           /* sort classes of td_bound for the pruned sweep; <= 0: default (8) */
+  float margin;                /* slack of the projection bound; <= 0: default (1e-5) */
+  int32_t rank, world;         /* world <= 1: single GPU */
+} dbb_knn_params;
+
+typedef struct {
+  int64_t cap_rows;            /* in: rows the arrays below can hold (n for world <= 1; >= 128 * ceil(ceil(n/128)/world) else) */
+  int64_t* row_ids;            /* [cap_rows] original id of output row r; may be NULL when world <= 1 (row r = scaffold r) */
+  int32_t* knn_idx;            /* [cap_rows][k] */
+  float* knn_dist;             /* [cap_rows][k] */
+  int32_t* count;              /* [cap_rows] or NULL */
+  int64_t* neighbour_bp;       /* [cap_rows] or NULL */
+  int64_t n_rows;              /* out: rows written */
+  int64_t tiles_visited, tiles_total;   /* out: 128 x 128 tiles executed / in this rank's share of the pair matrix */
+  int32_t pruned;              /* out: 1 if the tile-skipping sweep ran */
+  int32_t launches;            /* out: kernels launched by the call */
+  float ms_plan, ms_sweep, ms_second;   /* out: device time of planning, first sweep, second plan + sweep + merge */
+} dbb_knn_output;
+
+/* all pointers of `in` and `out` are DEVICE pointers (in->sig is [n][DBB_SIG_STRIDE], 16-byte aligned) */
+int dbb_knn_dev(dbb_ctx* ctx, const dbb_pairs_input* in, const dbb_knn_params* par, dbb_knn_output* out, void* stream);
+/* all pointers are HOST pointers (in->sig is dense [n][136] float32); runs on the context's own stream */
+int dbb_knn_host(dbb_ctx* ctx, const dbb_pairs_input* in_host, const dbb_knn_params* par, dbb_knn_output* out_host);
 
 /* ---- "next" row N1: rectangular filtered nearest-core search -- refineBins.py:42-96 (__workerThread), the same
  * ---- loop in unbinned.py:156-176.  For every unbinned contig u over all cores c (in array order):

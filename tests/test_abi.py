@@ -112,3 +112,43 @@ def test_product_never_imports_the_oracle():
         for f in files:
             if f.endswith(('.py', '.cu', '.cuh')):
                 assert 'oracle' not in open(os.path.join(dirpath, f)).read(), f
+
+
+@pytest.mark.gpu
+def test_knn_host_from_plain_numpy_and_contexts():
+    """The default kNN path through the C ABI alone: numpy buffers in, numpy buffers out, no torch (``dbb_knn_host``), on
+    the default context and on an explicit one; a context refuses to run with another device current."""
+    import ctypes
+    from dbb_b200 import _lib, _pairs, synthetic
+    from dbb_b200.data import load_td_dist
+    from dbb_b200.distributions import PairTables
+    from dbb_b200.genomicSignatures import GenomicSignatures
+    from oracle import dbb_oracle as O, checks
+    meta = synthetic.make_metagenome(seed=71, n_scaffolds=1500, min_len=1000, max_len=30000, n_genomes=10)
+    counts, freq = GenomicSignatures(4, 1).signatures(synthetic.generate_sequences(meta))
+    td = load_td_dist()
+    tables = PairTables(meta.length, tdDist=td, tdDistPer=80)
+    a = _pairs.run_knn_host(freq, tables, k=20, prune=1)
+    b = _pairs.run_knn_host(freq, tables, k=20, prune=0)
+    assert a['pruned'] and not b['pruned'] and 0 < a['tiles_visited'] <= a['tiles_total']   # (12 tiles: the unfiltered top-k visits them all)
+    for key in ('idx', 'dist', 'count', 'neighbour_bp', 'row_ids'):
+        assert np.array_equal(a[key], b[key]), key
+    rows = list(range(0, meta.n_scaffolds, 25))
+    checks.check_knn_sample(rows, a['idx'][rows], a['dist'][rows], a['count'][rows], a['neighbour_bp'][rows], freq, meta.length, 20,
+                            O.DistTables(tdDist=td, tdDistPer=80))
+    L = _lib.lib()
+    ctx = ctypes.c_void_p()
+    _lib.check(L.dbb_ctx_create(-1, ctypes.byref(ctx)))
+    try:
+        c = _pairs.run_knn_host(freq, tables, k=20, prune=1, ctx=ctx)
+        for key in ('idx', 'dist', 'count', 'neighbour_bp'):
+            assert np.array_equal(a[key], c[key]), key
+        # two ranks through the host entry point: disjoint rows, together everything
+        parts = [_pairs.run_knn_host(freq, tables, k=20, prune=1, rank=r, world=2, ctx=ctx) for r in range(2)]
+        ids = np.concatenate([p_['row_ids'] for p_ in parts])
+        assert np.array_equal(np.sort(ids), np.arange(meta.n_scaffolds))
+        for p_ in parts:
+            assert np.array_equal(p_['idx'], a['idx'][p_['row_ids']]) and np.array_equal(p_['count'], a['count'][p_['row_ids']])
+    finally:
+        _lib.check(L.dbb_ctx_destroy(ctx))
+    assert L.dbb_ctx_create(10 ** 6, ctypes.byref(ctx)) != 0 and b'no such device' in L.dbb_last_error()

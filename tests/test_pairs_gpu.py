@@ -316,14 +316,6 @@ def test_pruned_sweep_equals_full_sweep():
         for key in ('idx', 'dist', 'count', 'neighbour_bp'):
             assert torch.equal(part[key], full3[key][ids]), (key, rank)
     assert bool(seen.all())
-    # row blocks of the sorted order: together they are the full result
-    dt = device.DevicePairTables(cases[0][0])
-    full = device.pairs(sig, dt, k=20, want_count=True)
-    for r0, r1 in ((0, 900), (900, 1700), (1700, n)):
-        part = device.pairs_pruned(sig, dt, r0, r1, k=20, want_count=True)
-        ids = part['row_ids']
-        for key in ('idx', 'dist', 'count', 'neighbour_bp'):
-            assert torch.equal(part[key], full[key][ids]), (key, r0)
 
 
 def test_pruned_sweep_with_nan_signatures_and_ranks_beyond_the_row_tiles():
@@ -384,3 +376,72 @@ def test_tdneighbours_knn_public_api_pruned_and_plain_agree_with_the_oracle():
                                gcDistPer=80, covDist=cvd, covDistPer=80, prune=False)
     for x, y in zip(c, d):
         assert np.array_equal(x, y)
+
+
+def test_pruned_sweep_refuses_signatures_that_do_not_sum_to_one():
+    """The tile-skipping bound L1 >= 2|p_a - p_b| needs rows that sum to 1.  Raw counts (or rows zeroed by nan_to_num)
+    break it: the library counts such rows on the device and fails the call (prune=1 / prune=True), or runs the exact
+    full sweep instead (prune=-1 / the default of TdNeighbours.knn) -- never a silently wrong neighbour list."""
+    import torch
+    from dbb_b200 import _lib, device
+    from dbb_b200.distributions import PairTables
+    from dbb_b200.tdNeighbours import TdNeighbours
+    meta, sig64 = _metagenome(61, 1200, gmax=30000)
+    td, _, _ = _dists()
+    bad = sig64.copy()
+    bad[5] *= 1.5                                                       # sums to 1.5
+    bad[700] = 0.0                                                      # a NaN row that somebody zeroed
+    tables = PairTables(meta.length, tdDist=td, tdDistPer=80)
+    dt = device.DevicePairTables(tables)
+    sig = device.pad_signatures(torch.from_numpy(bad.astype(np.float32)).cuda())
+    with pytest.raises(_lib.DbbError, match='do not sum to 1'):
+        device.pairs_pruned(sig, dt, k=20, want_count=True)
+    full = device.pairs(sig, dt, k=20, want_count=True)
+    auto = device.pairs_pruned(sig, dt, k=20, want_count=True, prune=-1)
+    assert not auto['pruned']
+    for key in ('idx', 'dist', 'count', 'neighbour_bp'):
+        assert torch.equal(auto[key], full[key]), key
+    with pytest.raises(_lib.DbbError, match='do not sum to 1'):
+        TdNeighbours(None).knn(bad, meta.length, k=20, tdDist=td, tdDistPer=80, prune=True)
+    a = TdNeighbours(None).knn(bad, meta.length, k=20, tdDist=td, tdDistPer=80)                  # auto: full sweep
+    b = TdNeighbours(None).knn(bad, meta.length, k=20, tdDist=td, tdDistPer=80, prune=False)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    # rows that sum to 1 within float32 rounding pass, NaN rows are exempt
+    ok = sig64.copy()
+    ok[9] = np.nan
+    good = device.pairs_pruned(device.pad_signatures(torch.from_numpy(ok.astype(np.float32)).cuda()), dt, k=20, want_count=True)
+    assert good['pruned']
+
+
+def test_c4_law_eight_ranks_against_the_oracle():
+    """BASELINE.json configs[3] at reduced scale (30 000 scaffolds of the C4 length law, 1-14 kb, 2 000 genomes): the
+    pruned sweep dealt to 8 ranks (each emulated on this GPU) covers every row exactly once, and a row sample of every
+    rank agrees with the oracle's float64 rows (tdNeighbours.py:41-51) -- top-k within the tie band, counts, base pairs."""
+    import torch
+    from dbb_b200 import device, synthetic
+    from dbb_b200.data import load_td_dist
+    from dbb_b200.distributions import PairTables
+    from oracle import checks
+    meta = synthetic.make_config('C4', 0.03)
+    d_ascii, seq_off = device.synth_ascii(meta)
+    packed = device.pack_ascii(d_ascii, seq_off)
+    n = meta.n_scaffolds
+    freq = torch.zeros((n, 140), dtype=torch.float32, device='cuda')
+    device.CountPlan(packed).run(None, freq)
+    td = load_td_dist()
+    dt = device.DevicePairTables(PairTables(meta.length, tdDist=td, tdDistPer=80))
+    ot = O.DistTables(tdDist=td, tdDistPer=80)
+    sig32 = freq[:, :136].cpu().numpy()
+    seen = torch.zeros(n, dtype=torch.int32, device='cuda')
+    rng = np.random.RandomState(4)
+    for rank in range(8):
+        part = device.pairs_pruned(freq, dt, k=20, want_count=True, part=(rank, 8))
+        ids = part['row_ids']
+        seen[ids] += 1
+        pos = np.sort(rng.choice(int(ids.numel()), 12, replace=False))
+        tp = torch.from_numpy(pos).cuda()
+        checks.check_knn_sample(ids[tp].cpu().numpy(), part['idx'][tp].cpu().numpy(), part['dist'][tp].cpu().numpy(),
+                                part['count'][tp].cpu().numpy(), part['neighbour_bp'][tp].cpu().numpy(), sig32, meta.length, 20, ot)
+        assert part['tiles_visited'] < part['tiles_total']
+    assert bool((seen == 1).all())
