@@ -317,16 +317,23 @@ def run_ours(args):
     total_bp = int(meta.length.sum())
     counts = torch.zeros((my_n, 136), dtype=torch.int32, device=dev)
     freq = torch.zeros((my_n, _lib.SIG_STRIDE), dtype=torch.float32, device=dev)
+    # K1 -> K2 hand-off of the per-scaffold scalars: a rank contributes its own shard's (id, length, GC, coverage) and
+    # builds the tables of stage 2 from the gathered arrays (single GPU: its own arrays)
+    g_ids, g_len, g_gc, g_cov = order, meta.length[order], meta.gc_obs[order], meta.coverage[order]
+    if world > 1 and not counting_only:
+        g_ids, g_len, g_gc, g_cov = parallel.all_gather_scalars(mine, my_meta.length, my_meta.gc_obs, my_meta.coverage,
+                                                                counts=[len(p) for p in parts], device=dev)
+        assert np.array_equal(g_ids, order)
     if counting_only:
         tables = dt = None
         topk_filter = 0
     elif args.workload == 'C3':      # BASELINE.json configs[2]: all three predicates; top-k restricted by the GC and coverage filters
-        tables = PairTables(meta.length[order], GC=meta.gc_obs[order], coverage=meta.coverage[order], tdDist=load_td_dist(),
+        tables = PairTables(g_len, GC=g_gc, coverage=g_cov, tdDist=load_td_dist(),
                             tdDistPer=TD_PER, gcDist=synthetic.synthetic_gc_dist(), gcDistPer=TD_PER,
                             covDist=synthetic.synthetic_cov_dist(seed=3), covDistPer=TD_PER)
         topk_filter = device.FILTER_GC | device.FILTER_COV
     else:
-        tables = PairTables(meta.length[order], tdDist=load_td_dist(), tdDistPer=TD_PER)
+        tables = PairTables(g_len, tdDist=load_td_dist(), tdDistPer=TD_PER)
         topk_filter = 0
     if not counting_only:
         dt = device.DevicePairTables(tables, dev)

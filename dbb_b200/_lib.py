@@ -73,7 +73,7 @@ class KnnParams(ctypes.Structure):
 
 class KnnOutput(ctypes.Structure):
     _fields_ = [('cap_rows', c_i64), ('row_ids', c_vp), ('knn_idx', c_vp), ('knn_dist', c_vp), ('count', c_vp),
-                ('neighbour_bp', c_vp), ('n_rows', c_i64), ('tiles_visited', c_i64), ('tiles_total', c_i64),
+                ('neighbour_bp', c_vp), ('n_rows', c_i64), ('tiles_visited', c_i64), ('tiles_total', c_i64), ('tiles_second', c_i64), ('row_tiles_second', c_i64),
                 ('pruned', c_i32), ('launches', c_i32), ('ms_plan', ctypes.c_float), ('ms_sweep', ctypes.c_float),
                 ('ms_second', ctypes.c_float)]
 

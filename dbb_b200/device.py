@@ -241,6 +241,7 @@ def pairs_pruned(sig_padded, dt, k=20, topk_filter=0, want_count=True, metric='l
         res[key] = res[key][:rows]
     res['tiles_visited'], res['tiles_total'] = int(out.tiles_visited), int(out.tiles_total)
     res['launches'], res['pruned'] = int(out.launches), bool(out.pruned)
+    res['tiles_second'], res['row_tiles_second'] = int(out.tiles_second), int(out.row_tiles_second)
     ms = {'plan': float(out.ms_plan), 'sweep': float(out.ms_sweep), 'second sweep + merge': float(out.ms_second)}
     if isinstance(timings, list):
         timings.append(ms)

@@ -2,8 +2,8 @@
 
 Stage 1 (counting) shards by independent scaffolds: longest-processing-time-first over total base pairs,
 the same heuristic the reference uses for its worker processes (preprocess.py:373-387).  No collective.
-Hand-off: ONE all-gather of the float32 signature matrix (plus nothing else: per-scaffold scalars are
-host-known on every rank).  Stage 2 (pairs / kNN) shards by equal row blocks over the gathered order;
+Hand-off: ONE all-gather of the float32 signature matrix plus one of the per-scaffold scalars (length,
+GC, coverage, original id: ``all_gather_scalars``), so a rank only ever needs the metadata of its own shard.  Stage 2 (pairs / kNN) shards by equal row blocks over the gathered order;
 every rank reads all columns; per-row results are disjoint, so there is no reduction afterwards.
 
 All partition logic is pure host code (tested on CPU with gloo, world_size 2).
@@ -73,3 +73,28 @@ def all_gather_rows(local, counts, group=None):
     if all(int(c) == n_max for c in counts):
         return buf.view(world * n_max, width)
     return torch.cat([buf[r, :int(counts[r])] for r in range(world)], dim=0)
+
+
+def all_gather_scalars(ids, length, gc=None, coverage=None, counts=None, device=None, group=None):
+    """The K1 -> K2 hand-off of the per-scaffold scalars: every rank contributes the original ids,
+    lengths and (optionally) GC / coverage of ITS shard only; all ranks get the arrays of all scaffolds in gathered
+    order (rank-major, the order of ``all_gather_rows``).  One collective over a packed float64 [n, 4] record
+    (ids and lengths are exact in float64 up to 2^53).  ``counts[r]`` = scaffolds of rank r (every rank knows them: they
+    are the row counts of the signature gather).  Returns (ids int64, length int64, gc float64 | None, coverage | None)."""
+    import torch
+    ids = np.asarray(ids, dtype=np.int64)
+    rec = np.zeros((ids.shape[0], 4), dtype=np.float64)
+    rec[:, 0] = ids
+    rec[:, 1] = np.asarray(length, dtype=np.float64)
+    if gc is not None:
+        rec[:, 2] = gc
+    if coverage is not None:
+        rec[:, 3] = coverage
+    t = torch.from_numpy(rec)
+    if device is not None:
+        t = t.to(device)
+    if counts is None:
+        counts = [ids.shape[0]]
+    full = all_gather_rows(t, counts, group=group).cpu().numpy()
+    return (full[:, 0].astype(np.int64), full[:, 1].astype(np.int64), full[:, 2].copy() if gc is not None else None,
+            full[:, 3].copy() if coverage is not None else None)

@@ -281,6 +281,7 @@ typedef struct {
   int64_t* neighbour_bp;       /* [cap_rows] or NULL */
   int64_t n_rows;              /* out: rows written */
   int64_t tiles_visited, tiles_total;   /* out: 128 x 128 tiles executed / in this rank's share of the pair matrix */
+  int64_t tiles_second, row_tiles_second;   /* out: of those, tiles / row tiles of the second sweep */
   int32_t pruned;              /* out: 1 if the tile-skipping sweep ran */
   int32_t launches;            /* out: kernels launched by the call */
   float ms_plan, ms_sweep, ms_second;   /* out: device time of planning, first sweep, second plan + sweep + merge */

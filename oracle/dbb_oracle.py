@@ -855,3 +855,73 @@ def greedy_literal(sortedContigs, minBinSize, distributions):
                         contig.bProcessed = False
                         contig.binId = -1
     return cores
+
+
+def merge_literal(cores, distributions):
+    """greedy.py:258-333 (``Greedy.__merge``), statement for statement (progress output dropped; ``genomicSig.distance``
+    is ``distance`` above; ``distributions`` is built by the caller with mergeDistPer for all three tables as :256 does).
+    Sets ``bProcessed`` / ``binId`` on the input cores and ``binId`` on their contigs, returns the merged cores."""
+    for core in cores:
+        core.bProcessed = False
+    numMergedCores = 0
+    mergedCores = []
+    for coreIndex, core in enumerate(cores):
+        if core.bProcessed:
+            continue
+        core.bProcessed = True
+        curMergedCore = Core(numMergedCores, core.length, core.GC, core.coverage, core.tetraSig)
+        curMergedCore.contigs = core.contigs
+        bCoreMerged = True
+        while bCoreMerged:
+            closestCore = None
+            closestAbsCovDiff = 1e12
+            for curCore in cores[coreIndex + 1:]:
+                if curCore.bProcessed:
+                    continue
+                absCovDiff = abs(curCore.coverage - curMergedCore.coverage)
+                if absCovDiff > closestAbsCovDiff:
+                    continue
+                if not distributions.withinDistGC(curCore, curMergedCore):
+                    continue
+                if not distributions.withinDistCov(curCore, curMergedCore):
+                    continue
+                tdDistance = distance(curCore.tetraSig, curMergedCore.tetraSig)
+                if not distributions.witinDistTD(tdDistance, curCore):
+                    continue
+                closestAbsCovDiff = absCovDiff
+                closestCore = curCore
+            if closestCore is not None:
+                bCoreMerged = True
+                closestCore.bProcessed = True
+                closestCore.binId = numMergedCores
+                curMergedCore.contigs += closestCore.contigs
+                curMergedCore.length += closestCore.length
+                weight = float(closestCore.length) / curMergedCore.length
+                curMergedCore.GC = closestCore.GC * weight + curMergedCore.GC * (1.0 - weight)
+                curMergedCore.coverage = closestCore.coverage * weight + curMergedCore.coverage * (1.0 - weight)
+                for i in range(0, len(curCore.tetraSig)):
+                    curMergedCore.tetraSig[i] = closestCore.tetraSig[i] * weight + curMergedCore.tetraSig[i] * (1.0 - weight)
+            else:
+                bCoreMerged = False
+                numMergedCores += 1
+                mergedCores.append(curMergedCore)
+    for core in mergedCores:
+        for contig in core.contigs:
+            contig.binId = core.binId
+    return mergedCores
+
+
+def neighbourhood_sizes_literal(contigs):
+    """greedy.py:406-420 (``Greedy.__sortContigs``): base pairs of the common GC / TD / coverage neighbourhood of every
+    contig (attributes set by the three neighbour classes) and the order upstream computes and then drops (F8)."""
+    neighbourhoodSizes = []
+    for contig in contigs:
+        covNeighbours = np.where(contig.covNeighbours == 1)[0]
+        gcNeighbours = np.where(contig.gcNeighbours == 1)[0]
+        tdNeighbours = np.where(contig.tdNeighbours == 1)[0]
+        intersectCovGC = np.intersect1d(covNeighbours, gcNeighbours, assume_unique=True)
+        neighbourIndices = np.intersect1d(tdNeighbours, intersectCovGC, assume_unique=True)
+        totalNeighbourBPs = sum(contigs[i].length for i in neighbourIndices)
+        neighbourhoodSizes.append(totalNeighbourBPs)
+    sortedIndices = np.argsort(neighbourhoodSizes)[::-1]
+    return neighbourhoodSizes, sortedIndices

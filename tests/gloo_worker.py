@@ -25,6 +25,12 @@ def main():
     assert np.array_equal(full[:, 0].numpy(), order.astype(np.float32) * 3), 'gathered order is rank-major'
     # scalars permuted on the host line up with the gathered rows
     assert np.array_equal((full[:, 1].numpy() - 1) / 3, order)
+    # the scalar hand-off: every rank contributes the metadata of its own shard only
+    gc = rng.uniform(0.2, 0.8, 501)
+    cov = rng.lognormal(3.0, 1.0, 501)
+    ids, ln, g, c = parallel.all_gather_scalars(mine, lengths[mine], gc[mine], cov[mine], counts=[len(p) for p in parts])
+    assert np.array_equal(ids, order) and np.array_equal(ln, lengths[order])
+    assert np.array_equal(g, gc[order]) and np.array_equal(c, cov[order])
     r0, r1 = parallel.row_block(501, rank, world)
     rows = torch.tensor([float(r1 - r0)])
     dist.all_reduce(rows)

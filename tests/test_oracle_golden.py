@@ -195,6 +195,60 @@ def test_greedy_oracle_matches_reference_outputs():
         check_greedy_against_golden(g, tag, contigs, cores)
 
 
+def greedy_merge_case(tag):
+    """Input cores (with dummy contigs that remember their core) and the reference's own outputs of one golden __merge
+    case (tests/golden/make_golden_greedy_merge.py)."""
+    from dbb_b200 import synthetic
+    from dbb_b200.data import load_td_dist
+    g = util.golden_npz('ref_greedy_merge.npz')
+    cores = []
+    for b in range(len(g[tag + '_in_len'])):
+        core = O.Core(b, int(g[tag + '_in_len'][b]), float(g[tag + '_in_gc'][b]), float(g[tag + '_in_cov'][b]), g[tag + '_in_sig'][b].copy())
+        core.contigs = [_GContig(1, 0.5, 1.0, None) for _ in range(int(g[tag + '_in_sizes'][b]))]
+        for c in core.contigs:
+            c.binId = b
+        cores.append(core)
+    td = load_td_dist()
+    return g, cores, int(g[tag + '_params'][1]), synthetic.synthetic_gc_dist(sorted(td.keys())), td, synthetic.synthetic_cov_dist(seed=7)
+
+
+def check_merge_against_golden(g, tag, cores, merged):
+    assert np.array_equal(np.array([c.binId for c in cores]), g[tag + '_core_bin'])
+    assert len(merged) == len(g[tag + '_out_len']) < len(cores)
+    for b, m in enumerate(merged):
+        assert m.binId == b
+        assert m.length == g[tag + '_out_len'][b] and m.GC == g[tag + '_out_gc'][b] and m.coverage == g[tag + '_out_cov'][b]
+        assert np.array_equal(np.asarray(m.tetraSig), g[tag + '_out_sig'][b])             # same float64 operations, same order
+        assert len(m.contigs) == g[tag + '_out_sizes'][b] and all(c.binId == b for c in m.contigs)
+    # (a seed core keeps the binId __greedy gave it -- upstream only renumbers the cores it absorbs, greedy.py:311 -- so
+    # _core_bin holds old ids for the seeds; the contigs carry the merged ids, checked above)
+    assert int(g[tag + '_out_sizes'].sum()) == int((g[tag + '_contig_bin'] >= 0).sum())
+
+
+def test_greedy_merge_and_sort_oracle_match_reference_outputs():
+    """Rest of the N3 row: the literal restatements of greedy.py:258-333 (__merge) and :406-420 (neighbourhood sizes of
+    __sortContigs) reproduce what the reference's own source produced."""
+    for tag in ('a', 'b'):
+        g, cores, per, gcDist, tdDist, covDist = greedy_merge_case(tag)
+        merged = O.merge_literal(cores, O.Distributions(gcDist, per, tdDist, per, covDist, per))
+        check_merge_against_golden(g, tag, cores, merged)
+    g = util.golden_npz('ref_greedy_merge.npz')
+    n = len(g['s_length'])
+    fixed, per = int(g['s_params'][0]), int(g['s_params'][1])
+    from dbb_b200 import synthetic
+    from dbb_b200.data import load_td_dist
+    td = load_td_dist()
+    ot = O.DistTables(synthetic.synthetic_gc_dist(sorted(td.keys())), per, td, per, synthetic.synthetic_cov_dist(seed=7), per)
+    rows = list(range(n))
+    contigs = [_GContig(int(g['s_length'][i]), float(g['s_gc'][i]), float(g['s_cov'][i]), g['s_sig'][i]) for i in rows]
+    for i, c in enumerate(contigs):
+        c.tdNeighbours = O.td_rows_np(g['s_sig'], g['s_length'], [i], ot, fixed)[0]
+        c.gcNeighbours = O.gc_rows_np(g['s_length'], g['s_gc'], [i], ot, fixed)[0]
+        c.covNeighbours = O.cov_rows_np(g['s_length'], g['s_cov'], [i], ot, fixed)[0]
+    sizes, order = O.neighbourhood_sizes_literal(contigs)
+    assert np.array_equal(np.array(sizes), g['s_sizes']) and np.array_equal(order, g['s_sorted'])
+
+
 def merge_case(tag):
     """(golden, contigs in file order with binId set, (gcPer, tdPer, covPer), gcDist, tdDist, covDist) of the N5 golden
     vectors (tests/golden/make_golden_merge.py)."""
