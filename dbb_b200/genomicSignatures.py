@@ -19,26 +19,28 @@ from . import _lib
 
 
 def _read_fasta(path):
-    """FASTA -> list of (id, str) in file order (seqUtils.py:46-69 keeps the text up to the first
-    whitespace as id and concatenates the lines; '.gz' is opened with gzip, seqUtils.py:49-50)."""
+    """FASTA -> list of (id, str), parsed exactly as ``seqUtils.readFasta`` (seqUtils.py:46-69) parses it:
+    the id is the header up to the first SPACE (tabs stay in it), right-stripped; every sequence line loses its LAST
+    character whatever it is (``line[0:-1]``: the newline normally -- a '\r' of a CRLF file stays in the sequence and
+    invalidates the windows it touches, an unterminated last line loses a base); a repeated id REPLACES the earlier
+    record (``seqs[seqId] = []``); '.gz' is opened with gzip (:49-50).  Any failure -- unreadable file, sequence text
+    before the first header -- is the reference's log + ``sys.exit()`` (:64-67).  Order: first appearance of each id
+    (the reference iterates a py2 dict and writes rows in completion order, i.e. in no defined order)."""
     opener = gzip.open if path.endswith('.gz') else open
-    seqs, cur_id, cur = [], None, []
+    seqs = {}
     try:
-        with opener(path, 'rt') as f:
+        with opener(path, 'rt', newline='\n') as f:          # py2 text mode on POSIX: lines end at '\n' only, nothing is translated
+            seqId = None
             for line in f:
-                if line.startswith('>'):
-                    if cur_id is not None:
-                        seqs.append((cur_id, ''.join(cur)))
-                    cur_id = line[1:].split(None, 1)[0] if len(line) > 1 and line[1:].strip() else ''
-                    cur = []
+                if line[0] == '>':
+                    seqId = line[1:].partition(' ')[0].rstrip()
+                    seqs[seqId] = []
                 else:
-                    cur.append(line.rstrip('\r\n'))
-        if cur_id is not None:
-            seqs.append((cur_id, ''.join(cur)))
-    except IOError:
-        logging.getLogger().error('  [Error] Failed to open: ' + path)     # seqUtils.py:64-67
+                    seqs[seqId].append(line[0:-1])
+    except Exception:
+        logging.getLogger().error('  [Error] Failed to process sequence file: ' + path)
         sys.exit()
-    return seqs
+    return [(seqId, ''.join(parts)) for seqId, parts in seqs.items()]
 
 
 def _format_value(x):

@@ -5,6 +5,7 @@ import subprocess
 import sys
 
 import numpy as np
+import pytest
 
 from oracle import dbb_oracle as O
 from tests import util
@@ -166,3 +167,20 @@ def test_merge_and_unbinned_host_sides_reproduce_the_reference_files_from_their_
             score = int(round(float(f[14]) * len(s.contigs)))
             table[spos[f[0]], bpos[f[4]]] = [int(x) for x in f[8:14]] + [score]
         assert Unbinned().formatTable(scaffolds, bins, table, minScaffoldLen) == text, tag
+
+
+def test_fasta_reader_parses_like_the_reference(tmp_path):
+    """``GenomicSignatures.calculate`` reads FASTA exactly as seqUtils.readFasta does (golden: the reference's own function
+    text, tests/golden/make_golden_fasta.py): ids up to the first space (tabs kept), the last character of every line
+    dropped (a CRLF's '\\r' stays, an unterminated last line loses a base), a repeated id replaces the earlier record."""
+    import io
+    from dbb_b200.genomicSignatures import _read_fasta
+    g = util.golden_json('ref_fasta.json')
+    path = str(tmp_path / 'in.fasta')
+    with io.open(path, 'w', newline='') as f:
+        f.write(g['fasta'])
+    got = dict(_read_fasta(path))
+    assert got == g['records']
+    assert '\r' in got['seq2'] and got['last'].endswith('AG') and got['seq1'].startswith('TTTT') and '' in got
+    with pytest.raises(SystemExit):
+        _read_fasta(str(tmp_path / 'missing.fasta'))
