@@ -398,7 +398,8 @@ def run_ours(args):
     else:
         launches_per_step = plan.launches + int(result['knn']['launches'])     # pairs + merge kernels of one or two sweeps
 
-    e2e_s = e2e_count_s = None
+    e2e_s = e2e_count_s = e2e_page_s = None
+    pageable_ok = True
     h2d = d2h = 0
     rows = r1 - r0
     if not args.no_e2e:
@@ -438,6 +439,18 @@ def run_ours(args):
         torch.cuda.synchronize(); barrier()
         e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
         e2e_count_s = max_over_ranks(tc / e2e_steps)
+        # the same stage-1 call with PAGEABLE numpy buffers (what GenomicSignatures.signatures hands over): the library
+        # stages them through its own pinned ring (csrc/host_api.cu::h2d_any)
+        a_page = np.array(a_np)
+        pc, pf = np.empty((my_n, 136), dtype=np.uint32), np.empty((my_n, 136), dtype=np.float32)
+        _lib.check(L.dbb_tetra_signatures_host(_lib.ptr(a_page), _lib.ptr(seq_off), my_n, _lib.ptr(pc), _lib.ptr(pf)))
+        barrier()
+        t1 = time.perf_counter()
+        for _ in range(3):
+            _lib.check(L.dbb_tetra_signatures_host(_lib.ptr(a_page), _lib.ptr(seq_off), my_n, _lib.ptr(pc), _lib.ptr(pf)))
+        e2e_page_s = max_over_ranks((time.perf_counter() - t1) / 3)
+        pageable_ok = bool(np.array_equal(pc, h_counts))
+        del a_page
         rows = r1 - r0
         h2d = int(a_np.nbytes + seq_off.nbytes * 2 + (n_total * 136 * 4 + n_total * 8 if world == 1 else my_n * 136 * 4))
         d2h = int(my_n * 136 * 8 + rows * (K_NN * 8 + 12))
@@ -458,7 +471,7 @@ def run_ours(args):
             s = d_ascii[int(seq_off[i]):int(seq_off[i + 1])].cpu().numpy()
             ok &= bool(np.array_equal(hc[i], O.seq_counts_np(s)))
         if not args.no_e2e:
-            ok &= bool(np.array_equal(h_counts.astype(np.int64), hc))
+            ok &= bool(np.array_equal(h_counts.astype(np.int64), hc)) and pageable_ok
         if not counting_only:
             # stage 2 against the ORACLE at this size (every N, every workload): a seeded sample of this rank's rows,
             # float64 distances to all n_total columns by the C restatement of tdNeighbours.py:41-51, predicates by the
@@ -546,7 +559,7 @@ def run_ours(args):
                            'peak_source': '%d SMs x 128 FP32 lanes x %.0f MHz (272 lane-ops per pair)' % (sm_count, sm_max_mhz)},
         'e2e': None if args.no_e2e else {'value': total_bp / e2e_count_s / 1e9, 'unit': 'Gbp/s', 'value2': pairs_total / max(e2e_s - e2e_count_s, 1e-9),
                 'unit2': 'scaffold-pairs/s', 'ms_per_step': e2e_s * 1e3, 'steps': e2e_steps,
-                'pipeline_gbp_per_s': total_bp / e2e_s / 1e9, 'pipeline_pairs_per_s': pairs_total / e2e_s,
+                'value_pageable_host_buffers': total_bp / e2e_page_s / 1e9, 'pipeline_gbp_per_s': total_bp / e2e_s / 1e9, 'pipeline_pairs_per_s': pairs_total / e2e_s,
                 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                 'api': 'dbb_tetra_signatures_host + dbb_pairs_host (pinned host buffers)' if args.no_prune else
                        'dbb_tetra_signatures_host + dbb_knn_host (pinned host buffers)' if world == 1 else 'dbb_tetra_signatures_host (pinned host buffers) + H2D of the signatures, all-gather, dbb_knn_dev, D2H of the results'},

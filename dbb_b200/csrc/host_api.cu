@@ -4,7 +4,10 @@
 #include "common.cuh"
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
+#include <atomic>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 namespace dbb {
@@ -20,9 +23,14 @@ int DevBuf::reserve(size_t bytes) {
 }
 void DevBuf::release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 
+constexpr size_t PIN_CHUNK = 4u << 20;   // staging ring for pageable input: 8 chunks of 4 MB per lane
+constexpr int PIN_SLOTS = 8;
+
 struct Lane {            // one in-flight batch of stage 1
   cudaStream_t st = nullptr;
   DevBuf ascii, seq_off, blk_off, codes, valid, counts, freq;
+  uint8_t* pin = nullptr;               // pinned ring (lazily allocated, only when a caller passes pageable memory)
+  cudaEvent_t pin_ev[PIN_SLOTS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   dbb_count_plan* plan = nullptr;
   int64_t s0 = 0, s1 = 0;
   std::vector<int64_t> h_off, h_blk;
@@ -38,6 +46,8 @@ void free_sig_state(SigState* s) {
   for (auto& L : s->lanes) {
     for (DevBuf* b : {&L.ascii, &L.seq_off, &L.blk_off, &L.codes, &L.valid, &L.counts, &L.freq}) b->release();
     if (L.plan) dbb_count_plan_destroy(L.plan);
+    if (L.pin) cudaFreeHost(L.pin);
+    for (auto& e : L.pin_ev) if (e) cudaEventDestroy(e);
     if (L.st) cudaStreamDestroy(L.st);
   }
   delete s;
@@ -126,10 +136,75 @@ namespace {
 
 using dbb::DevBuf;
 using dbb::Lane;
+using dbb::PIN_CHUNK;
+using dbb::PIN_SLOTS;
 
 #define DBB_TRY(expr) do { int _rc = (expr); if (_rc != DBB_OK) return _rc; } while (0)
 
-int submit_batch(Lane& L, const uint8_t* ascii, const int64_t* seq_off, int64_t s0, int64_t s1,
+// Host -> device copy of a range that may be PAGEABLE (a numpy array, a Python bytes object).  A pageable
+// cudaMemcpyAsync is staged by the driver on the calling thread at ~10 GB/s; here a few threads copy 4 MB chunks into
+// the lane's pinned ring and the chunks go up with asynchronous copies as they become ready, so the link stays busy.
+// Pinned / registered memory takes the direct path.
+int h2d_any(Lane& L, int device, void* dst, const uint8_t* src, size_t nbytes) {
+  if (nbytes == 0) return DBB_OK;
+  cudaPointerAttributes attr;
+  const bool pageable = cudaPointerGetAttributes(&attr, src) != cudaSuccess || attr.type == cudaMemoryTypeUnregistered;
+  cudaGetLastError();                                        // (an unknown host pointer is reported as an error on old drivers)
+  static const int n_threads = [] {
+    const char* e = getenv("DBB_HOST_THREADS");
+    int t = (e && *e) ? atoi(e) : (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
+    return std::max(1, std::min(t, 32));
+  }();
+  if (!pageable || nbytes < 2 * PIN_CHUNK || n_threads <= 1) {
+    DBB_CUDA_TRY(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyHostToDevice, L.st));
+    return DBB_OK;
+  }
+  if (!L.pin) {
+    DBB_CUDA_TRY(cudaHostAlloc((void**)&L.pin, PIN_CHUNK * PIN_SLOTS, cudaHostAllocDefault));
+    for (auto& e : L.pin_ev) DBB_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  const int n_chunks = (int)((nbytes + PIN_CHUNK - 1) / PIN_CHUNK);
+  std::vector<std::atomic<int>> ready(n_chunks), issued(n_chunks);
+  for (int c = 0; c < n_chunks; ++c) { ready[c].store(0); issued[c].store(0); }
+  std::atomic<int> next{0}, failed{0};
+  auto worker = [&]() {
+    cudaSetDevice(device);
+    for (;;) {
+      const int c = next.fetch_add(1);
+      if (c >= n_chunks || failed.load()) break;
+      const int slot = c % PIN_SLOTS;
+      if (c >= PIN_SLOTS) {                                  // the slot's previous chunk must have left for the device
+        while (!issued[c - PIN_SLOTS].load(std::memory_order_acquire)) { if (failed.load()) return; std::this_thread::yield(); }
+      }
+      if (cudaEventSynchronize(L.pin_ev[slot]) != cudaSuccess) { failed.store(1); return; }
+      const size_t o = (size_t)c * PIN_CHUNK, len = std::min(PIN_CHUNK, nbytes - o);
+      memcpy(L.pin + (size_t)slot * PIN_CHUNK, src + o, len);
+      ready[c].store(1, std::memory_order_release);
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int t = 0; t < std::min(n_threads, n_chunks); ++t) pool.emplace_back(worker);
+  cudaError_t e = cudaSuccess;
+  for (int c = 0; c < n_chunks && e == cudaSuccess; ++c) {
+    while (!ready[c].load(std::memory_order_acquire)) { if (failed.load()) break; std::this_thread::yield(); }
+    if (failed.load()) break;
+    const int slot = c % PIN_SLOTS;
+    const size_t o = (size_t)c * PIN_CHUNK, len = std::min(PIN_CHUNK, nbytes - o);
+    e = cudaMemcpyAsync((uint8_t*)dst + o, L.pin + (size_t)slot * PIN_CHUNK, len, cudaMemcpyHostToDevice, L.st);
+    if (e == cudaSuccess) e = cudaEventRecord(L.pin_ev[slot], L.st);
+    issued[c].store(1, std::memory_order_release);
+  }
+  if (e != cudaSuccess) failed.store(1);
+  for (int c = 0; c < n_chunks; ++c) issued[c].store(1, std::memory_order_release);     // release any waiting worker
+  for (auto& th : pool) th.join();
+  if (e != cudaSuccess || failed.load()) {
+    dbb::set_error("staged host-to-device copy failed: %s", cudaGetErrorString(e != cudaSuccess ? e : cudaGetLastError()));
+    return DBB_ERR_CUDA;
+  }
+  return DBB_OK;
+}
+
+int submit_batch(Lane& L, int device, const uint8_t* ascii, const int64_t* seq_off, int64_t s0, int64_t s1,
                  bool want_counts, bool want_freq) {
   const int64_t ns = s1 - s0;
   const int64_t byte0 = seq_off[s0], nbytes = seq_off[s1] - byte0;
@@ -154,7 +229,7 @@ int submit_batch(Lane& L, const uint8_t* ascii, const int64_t* seq_off, int64_t 
   if (want_freq) DBB_TRY(L.freq.reserve((size_t)ns * DBB_NUM_KMERS * 4));
   if (!L.plan) DBB_TRY(dbb_count_plan_create(L.h_blk.data(), ns, &L.plan));
   else DBB_TRY(dbb::count_plan_rebuild(L.plan, L.h_blk.data(), ns, L.st));
-  if (nbytes) DBB_CUDA_TRY(cudaMemcpyAsync(L.ascii.p, ascii + byte0, nbytes, cudaMemcpyHostToDevice, L.st));
+  DBB_TRY(h2d_any(L, device, L.ascii.p, ascii + byte0, (size_t)nbytes));
   DBB_CUDA_TRY(cudaMemcpyAsync(L.seq_off.p, L.h_off.data(), (ns + 1) * 8, cudaMemcpyHostToDevice, L.st));
   DBB_CUDA_TRY(cudaMemcpyAsync(L.blk_off.p, L.h_blk.data(), (ns + 1) * 8, cudaMemcpyHostToDevice, L.st));
   DBB_TRY(dbb_pack_ascii_dev((const uint8_t*)L.ascii.p, (const int64_t*)L.seq_off.p, (const int64_t*)L.blk_off.p, ns,
@@ -208,7 +283,7 @@ DBB_EXPORT int dbb_tetra_signatures_host(const uint8_t* ascii, const int64_t* se
     while (e < n_seq && (e == s || seq_off[e + 1] - b0 <= batch_bytes)) ++e;
     Lane& L = lanes[cur];
     if (pending[cur]) { rc = collect_batch(L, counts, freq); pending[cur] = false; if (rc != DBB_OK) break; }
-    rc = submit_batch(L, ascii, seq_off, s, e, counts != nullptr, freq != nullptr);
+    rc = submit_batch(L, ctx->device, ascii, seq_off, s, e, counts != nullptr, freq != nullptr);
     if (rc != DBB_OK) break;
     pending[cur] = true;
     cur ^= 1;

@@ -1048,14 +1048,14 @@ DBB_EXPORT int dbb_pairs_dev(const dbb_pairs_input* in, int64_t row0, int64_t ro
   total = off_bp + (size_t)rem * TILE * n_seg * 8;
   // stream-ordered scratch; keep freed blocks cached in the device pool instead of returning them to the
   // driver at every synchronisation (the default release threshold is 0)
-  static bool pool_configured = false;
-  if (!pool_configured) {
+  static bool pool_configured[64] = {false};       // per device ordinal
+  if (dev >= 0 && dev < 64 && !pool_configured[dev]) {
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
       uint64_t keep = ~0ull;
       cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
-    pool_configured = true;
+    pool_configured[dev] = true;
   }
   uint8_t* scratch = nullptr;
   DBB_CUDA_TRY(cudaMallocAsync((void**)&scratch, total, st));

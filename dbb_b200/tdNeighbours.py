@@ -6,6 +6,12 @@
 row is attached as ``seqs[i].tdNeighbours``.  ``threads`` is accepted and ignored.  The N x N work runs
 in the fused distance kernel (csrc/pairs.cu); only the bit mask comes back.
 
+Precision (stated deviation): the reference compares a float64 distance with a float64 bound; here signatures are
+float32, the 136 terms are accumulated in FP32 and the bound is rounded to float32, so ``|d32 - d64| <= 2e-6`` and a pair
+whose float64 distance lies within 2e-6 of its bound may fall on the other side (measured on the synthetic configs:
+0-4 such pairs per 4 million; tests/ assert exact equality outside that band).  The GC and coverage predicates are
+evaluated in FP64 on the device and are exact.
+
 ``knn`` is the array-native addition (not in the reference): fused per-row top-k plus the size of the
 common neighbourhood that greedy.py:407-417 derives from the three masks.
 """
