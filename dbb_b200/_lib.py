@@ -28,7 +28,7 @@ class PairsInput(ctypes.Structure):
                 ('gc_nm', c_i32), ('gc_nl', c_i32),
                 ('cov', c_vp), ('cov_lbin', c_vp), ('cov_lo', c_vp), ('cov_hi', c_vp), ('cov_nl', c_i32),
                 ('metric', c_i32), ('col_id', c_vp), ('item_order', c_vp), ('tile_off', c_vp), ('tile_list', c_vp),
-                ('split_all', c_i32), ('n_active_row_tiles', c_i32)]
+                ('split_all', c_i32), ('n_active_row_tiles', c_i32), ('split_tiles', c_i32), ('reserved0', c_i32)]
 
 
 METRICS = {'l1': 0, 'manhattan': 0, 'l2': 1, 'euclidean': 1}

@@ -332,7 +332,7 @@ DBB_EXPORT int dbb_pairs_host(const dbb_pairs_input* in, int64_t row0, int64_t r
   dbb_pairs_input d = *in;
   dbb_pairs_output o = *out;
   d.col_id = nullptr; d.item_order = nullptr; d.tile_off = nullptr; d.tile_list = nullptr;   // device-path options
-  d.split_all = 0; d.n_active_row_tiles = 0;
+  d.split_all = 0; d.n_active_row_tiles = 0; d.split_tiles = 0;
   do {
     // NOTE: on the host side `sig` is dense [n][136]
     if ((rc = to_dev(dense, in->sig, n * DBB_NUM_KMERS, st)) != DBB_OK) break;

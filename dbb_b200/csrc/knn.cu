@@ -171,7 +171,7 @@ int full_sweep(const dbb_pairs_input* in, const dbb_knn_params* par, dbb_knn_out
   const int64_t r0 = (n * rank) / world, r1 = (n * (rank + 1)) / world;
   DBB_REQUIRE(out->cap_rows >= r1 - r0, "cap_rows too small");
   dbb_pairs_input d = *in;
-  d.col_id = nullptr; d.item_order = nullptr; d.tile_off = nullptr; d.tile_list = nullptr; d.split_all = 0; d.n_active_row_tiles = 0;
+  d.col_id = nullptr; d.item_order = nullptr; d.tile_off = nullptr; d.tile_list = nullptr; d.split_all = 0; d.n_active_row_tiles = 0; d.split_tiles = 0;
   dbb_pairs_output o = {};
   o.k = par->k; o.topk_filter = par->topk_filter;
   o.knn_idx = out->knn_idx; o.knn_dist = out->knn_dist; o.count = out->count; o.neighbour_bp = out->neighbour_bp;
@@ -292,7 +292,14 @@ DBB_EXPORT int dbb_knn_dev(dbb_ctx* ctx_in, const dbb_pairs_input* in, const dbb
   d.sig = pb.sig_sorted; d.length = pb.length; d.td_bound = pb.td_bound; d.gc = pb.gc; d.gc_mbin = pb.gc_mbin; d.gc_lbin = pb.gc_lbin;
   d.cov = pb.cov; d.cov_lbin = pb.cov_lbin;
   d.col_id = pb.col_id; d.item_order = pb.item_order; d.tile_off = pb.tile_off; d.tile_list = pb.tile_list;
-  d.split_all = split_for(n_mine, items_target);
+  // Work items: every row tile in split_for(...) strided segments (~5 items per SM).  The sweep ends with its longest
+  // item (C2: 782 items, the last CTA finishing 10 % after the mean), but cutting the long lists more finely
+  // (dbb_pairs_input.split_tiles; DBB_PRUNE_SEG_TILES=<tiles per segment> to try it) costs more than it evens out: every
+  // segment re-converges its own top-k thresholds (C2: 24 / 45 / 96 tiles per segment -> 14.7 / 13.6 / 13.5 ms against
+  // 12.2 ms for the uniform split, profiles/r02_k2_notes.md).
+  static const int64_t seg_env = [] { const char* e = getenv("DBB_PRUNE_SEG_TILES"); return (e && *e) ? atoll(e) : 0ll; }();
+  if (seg_env <= 0) { d.split_all = split_for(n_mine, items_target); d.split_tiles = 0; }
+  else { d.split_all = 8; d.split_tiles = (int32_t)std::min<int64_t>(seg_env, 1 << 30); }
   d.n_active_row_tiles = world > 1 ? (int32_t)n_mine : 0;
   dbb_pairs_output o = {};
   o.k = k; o.topk_filter = par->topk_filter;
@@ -335,6 +342,7 @@ DBB_EXPORT int dbb_knn_dev(dbb_ctx* ctx_in, const dbb_pairs_input* in, const dbb
       // long as its longest item, so lists are cut into pieces of <= ~32 tiles (C3: 11.3 -> 2 ms, at any GPU count)
       d2.split_all = (int)std::min<int64_t>(64, std::max<int64_t>(split_for(n_aff, 2 * items_target), (n_ct + 31) / 32));
       d2.n_active_row_tiles = (int32_t)n_aff;
+      d2.split_tiles = 0;
       dbb_pairs_output o2 = {};
       o2.k = k; o2.topk_filter = par->topk_filter;
       o2.knn_idx = (int32_t*)K.s2_idx.p; o2.knn_dist = (float*)K.s2_dist.p;
@@ -401,7 +409,7 @@ DBB_EXPORT int dbb_knn_host(dbb_ctx* ctx_in, const dbb_pairs_input* in, const db
   const size_t k = (size_t)par->k;
   const size_t cap = (size_t)out->cap_rows;
   dbb_pairs_input d = *in;
-  d.col_id = nullptr; d.item_order = nullptr; d.tile_off = nullptr; d.tile_list = nullptr; d.split_all = 0; d.n_active_row_tiles = 0;
+  d.col_id = nullptr; d.item_order = nullptr; d.tile_off = nullptr; d.tile_list = nullptr; d.split_all = 0; d.n_active_row_tiles = 0; d.split_tiles = 0;
   // on the host side `sig` is dense [n][136]
   DBB_TRY(to_dev(K.h_dense, in->sig, n * DBB_NUM_KMERS, st));
   DBB_TRY(K.h_sig.reserve(n * DBB_SIG_STRIDE * 4));

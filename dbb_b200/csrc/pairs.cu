@@ -86,6 +86,7 @@ struct Params {
   // work items: row tiles [0, n_full_rt) are swept over all columns by one CTA; each remaining row tile is
   // split into n_seg column segments (separate items) whose partial results are merged afterwards
   int32_t n_full_rt, n_seg, n_items, debug_skip_epilogue;
+  int32_t seg_tiles;        // > 0: a tile list of L entries uses min(n_seg, ceil(L / seg_tiles)) of its n_seg segment slots
   int32_t opaque_zero;         // always 0 (see the k4 loop)
   uint32_t* item_counter;
   unsigned long long* stats;   // profiling builds only (-DDBB_K2_STATS, run with DBB_K2_STATS=1): [0] queued pairs, [1] drains, [2] top-k candidates
@@ -609,13 +610,25 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pairs_kernel(const __grid_const
   const uint32_t lt_mask = (1u << lane) - 1u;
   uint32_t q = 0;          // B chunks consumed so far by this CTA (ring position / mbarrier phase)
   uint32_t items_done = 0;
+  if (P.stats && tid == 0 && blockIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    P.stats[8] = t;
+  }
 
   while (true) {
     __syncthreads();                       // everyone is done with the previous item's A tile and lists
     if (tid == 0) sm.item = (int32_t)atomicAdd(P.item_counter, 1u);
     __syncthreads();
     const int item = sm.item;
-    if (item >= P.n_items) break;
+    if (item >= P.n_items) {
+      if (P.stats && tid == 0 && blockIdx.x < 1000) {      // DBB_K2_STATS: when did this CTA run out of work
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        P.stats[16 + blockIdx.x] = t;
+      }
+      break;
+    }
     // work position -> row tile, segment of its tile sequence [t0, t1)
     int pos = item, seg = -1, srt = 0;
     if (item >= P.n_full_rt) {
@@ -631,12 +644,28 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pairs_kernel(const __grid_const
     // n_seg-th entry (the lists come nearest-first: every segment then sees near tiles early and its top-k
     // threshold tightens at once)
     const bool strided = P.tile_list != nullptr && seg >= 0;
-    const int t0 = (seg < 0 || strided) ? 0 : (int)(((int64_t)n_tiles * seg) / P.n_seg);
-    const int t1 = seg < 0 ? n_tiles : (strided ? (n_tiles - seg + P.n_seg - 1) / P.n_seg : (int)(((int64_t)n_tiles * (seg + 1)) / P.n_seg));
-    auto tile_at = [&](int t) -> int {
-      return P.tile_list ? __ldg(P.tile_list + list_base + (strided ? seg + t * P.n_seg : t)) : t;
-    };
+    // segments in use: all n_seg, or (seg_tiles > 0) as many as keep a segment near seg_tiles entries -- the sweep ends
+    // with its longest item, so long lists are cut finely, while short ones stay whole (every segment refills its own
+    // top-k lists); the unused slots of a row tile write empty partial results
+    int n_use = P.n_seg;
+    if (strided && P.seg_tiles > 0) n_use = max(1, min(P.n_seg, (n_tiles + P.seg_tiles - 1) / P.seg_tiles));
     const int64_t row_base = P.row0 + (int64_t)rt * TILE;
+    if (strided && seg >= n_use) {
+      for (int lr = tid; lr < TILE; lr += WARPS * 32) {
+        if (row_base + lr < P.row1) {
+          const int64_t o = ((int64_t)srt * TILE + lr) * P.n_seg + seg;
+          P.part_cnt[o] = 0;
+          P.part_bp[o] = 0;
+          if (F_TOPK) for (int e = 0; e < P.k; ++e) { P.part_idx[o * P.k + e] = INT_MAX; P.part_dist[o * P.k + e] = INFINITY; }
+        }
+      }
+      continue;
+    }
+    const int t0 = (seg < 0 || strided) ? 0 : (int)(((int64_t)n_tiles * seg) / P.n_seg);
+    const int t1 = seg < 0 ? n_tiles : (strided ? (n_tiles - seg + n_use - 1) / n_use : (int)(((int64_t)n_tiles * (seg + 1)) / P.n_seg));
+    auto tile_at = [&](int t) -> int {
+      return P.tile_list ? __ldg(P.tile_list + list_base + (strided ? seg + t * n_use : t)) : t;
+    };
     const uint32_t item_chunks = (uint32_t)(t1 - t0) * NKC;
     const uint32_t qbase = q;
 
@@ -994,7 +1023,7 @@ DBB_EXPORT int dbb_pairs_dev(const dbb_pairs_input* in, int64_t row0, int64_t ro
   DBB_REQUIRE(!out->td_mask || in->td_bound, "td_mask requested without td_bound");
   DBB_REQUIRE((in->tile_off == nullptr) == (in->tile_list == nullptr), "tile_off and tile_list go together");
   DBB_REQUIRE(!in->tile_off || !masks, "masks need every column tile: not available with a sparse sweep (tile_off / tile_list)");
-  DBB_REQUIRE(in->split_all >= 0 && in->split_all <= 64 && in->n_active_row_tiles >= 0, "bad split_all / n_active_row_tiles");
+  DBB_REQUIRE(in->split_all >= 0 && in->split_all <= 64 && in->n_active_row_tiles >= 0 && in->split_tiles >= 0, "bad split_all / n_active_row_tiles / split_tiles");
   DBB_REQUIRE(in->n_active_row_tiles == 0 || in->item_order, "n_active_row_tiles needs item_order");
 
   EncodeTiledFn encode;
@@ -1036,12 +1065,13 @@ DBB_EXPORT int dbb_pairs_dev(const dbb_pairs_input* in, int64_t row0, int64_t ro
   else plan_items(n_rt_active, n_ct, sms, &n_full, &rem, &n_seg);
   P.n_full_rt = (int32_t)n_full;
   P.n_seg = n_seg;
+  P.seg_tiles = (in->split_all > 0 && in->tile_list) ? in->split_tiles : 0;
   P.n_items = (int32_t)(n_full + rem * n_seg);
   P.opaque_zero = 0;
   { const char* e2 = getenv("DBB_K2_DEBUG_SKIP_EPILOGUE"); P.debug_skip_epilogue = (e2 && *e2) ? atoi(e2) : 0; }   // profiling only
   const int64_t split_rows = rem * TILE;          // merge_kernel skips the rows of a last, partial row tile itself
   const size_t k_ = (size_t)std::max(out->k, 1);
-  size_t off_idx = 256, off_dist, off_cnt, off_bp, total;
+  size_t off_idx = 8192, off_dist, off_cnt, off_bp, total;          // header: item counter, statistics (DBB_K2_STATS)
   off_dist = off_idx + (size_t)rem * TILE * n_seg * k_ * 4;
   off_cnt = off_dist + (size_t)rem * TILE * n_seg * k_ * 4;
   off_bp = (off_cnt + (size_t)rem * TILE * n_seg * 4 + 7) & ~(size_t)7;
@@ -1059,7 +1089,7 @@ DBB_EXPORT int dbb_pairs_dev(const dbb_pairs_input* in, int64_t row0, int64_t ro
   }
   uint8_t* scratch = nullptr;
   DBB_CUDA_TRY(cudaMallocAsync((void**)&scratch, total, st));
-  DBB_CUDA_TRY(cudaMemsetAsync(scratch, 0, 256, st));
+  DBB_CUDA_TRY(cudaMemsetAsync(scratch, 0, 8192, st));
   P.item_counter = (uint32_t*)scratch;
   static const bool want_stats = [] { const char* e = getenv("DBB_K2_STATS"); return e && *e == '1'; }();
   P.stats = want_stats ? (unsigned long long*)(scratch + 64) : nullptr;
@@ -1077,7 +1107,7 @@ DBB_EXPORT int dbb_pairs_dev(const dbb_pairs_input* in, int64_t row0, int64_t ro
     if (cudaGetLastError() != cudaSuccess) { dbb::set_error("merge kernel launch failed"); rc = DBB_ERR_CUDA; }
   }
   if (want_stats && rc == DBB_OK) {
-    unsigned long long h[6] = {0, 0, 0, 0, 0, 0};
+    static unsigned long long h[1024];
     cudaMemcpyAsync(h, scratch + 64, sizeof(h), cudaMemcpyDeviceToHost, st);
     cudaStreamSynchronize(st);
     const double pairs = (double)(row1 - row0) * (double)in->n;
@@ -1085,6 +1115,14 @@ DBB_EXPORT int dbb_pairs_dev(const dbb_pairs_input* in, int64_t row0, int64_t ro
     fprintf(stderr, "[dbb K2 stats] pairs %.3e queued %llu (%.4f %%) drains %llu top-k candidates %llu | warp cycles: distance loop "
             "%.1f %% hot test %.1f %% final drain %.1f %%\n", pairs, h[0], 100.0 * (double)h[0] / pairs, h[1], h[2],
             100.0 * h[3] / tt, 100.0 * h[4] / tt, 100.0 * h[5] / tt);
+    // when each CTA ran out of work, relative to the start of CTA 0 (us): the sweep ends with the last one
+    double mn = 1e30, mx = 0, sum = 0;
+    for (unsigned b = 0; b < grid && b < 1000; ++b) {
+      const double e = (double)(h[16 + b] - h[8]) * 1e-3;
+      mn = std::min(mn, e); mx = std::max(mx, e); sum += e;
+    }
+    fprintf(stderr, "[dbb K2 stats] items %d over %u CTAs: CTA finish times min %.0f mean %.0f max %.0f us (max / mean %.3f)\n",
+            P.n_items, grid, mn, sum / grid, mx, mx / (sum / grid));
   }
   cudaFreeAsync(scratch, st);
   return rc;

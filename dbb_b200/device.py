@@ -159,6 +159,7 @@ def pairs(sig_padded, dt, row0=0, row1=None, k=0, topk_filter=0, want_count=True
     if sparse is not None:
         inp.col_id, inp.item_order, inp.tile_off, inp.tile_list = (_p(t) for t in sparse[:4])
         inp.split_all, inp.n_active_row_tiles = int(sparse[4]), int(sparse[5])
+        inp.split_tiles = int(sparse[6]) if len(sparse) > 6 else 0
     if dt.gc is not None:
         inp.gc, inp.gc_mbin, inp.gc_lbin, inp.gc_lo, inp.gc_hi = _p(dt.gc), _p(dt.gc_mbin), _p(dt.gc_lbin), _p(dt.gc_lo), _p(dt.gc_hi)
         inp.gc_nm, inp.gc_nl = dt.gc_lo.shape

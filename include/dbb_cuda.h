@@ -171,6 +171,11 @@ typedef struct {
                                   library splits only the row tiles of the last partial wave */
   int32_t n_active_row_tiles;  /* > 0: only the first so many row tiles of item_order are processed (the outputs of
                                   the other rows are left untouched); 0: all */
+  int32_t split_tiles;         /* > 0 (with split_all and tile lists): a row tile whose list holds L tiles is cut into
+                                  min(split_all, ceil(L / split_tiles)) segments instead of split_all -- long lists are
+                                  cut finely (the sweep ends with its longest item), short ones not at all (every
+                                  segment refills its own top-k lists); 0: split_all segments for every row tile */
+  int32_t reserved0;
 } dbb_pairs_input;
 
 typedef struct {
