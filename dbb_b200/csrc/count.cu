@@ -436,6 +436,7 @@ struct dbb_count_plan {
   // per class (S = 1..4): item range in d_items
   uint32_t class_begin[4] = {0, 0, 0, 0};
   uint32_t class_count[4] = {0, 0, 0, 0};
+  uint32_t class_grid[4] = {0, 0, 0, 0};       // CTAs of the class kernel: CTA g takes items g, g + grid, ... of its class list
   Item* d_items = nullptr;
   size_t cap_items = 0;
   uint32_t n_split = 0;
@@ -468,24 +469,44 @@ int upload_tables() {
   return DBB_OK;
 }
 
+// The kernel instantiation of a class: warps per item (= per CTA) and minimum CTAs per SM are the measured best
+// (profiles/r02_k1_classes_by_length.txt); DBB_K1_WPI<S> overrides exist for tuning sweeps.
+struct ClassCfg { const void* fn; int threads; size_t smem; int S; };
 template <int S, int WPI, int MINB>
+ClassCfg make_cfg() {
+  return ClassCfg{(const void*)count_kernel<S, WPI, MINB>, 32 * WPI, (size_t)(256 + Geo<S>::WORDS + 160 + WPI * 16) * sizeof(uint32_t), S};
+}
+const ClassCfg& class_cfg(int c) {
+  static const ClassCfg cfg[4] = {
+      make_cfg<1, 1, 16>(),
+      env_i64("DBB_K1_WPI2", 2) >= 2 ? make_cfg<2, 2, 12>() : make_cfg<2, 1, 16>(),
+      env_i64("DBB_K1_WPI3", 2) >= 4 ? make_cfg<3, 4, 8>() : env_i64("DBB_K1_WPI3", 2) >= 2 ? make_cfg<3, 2, 12>() : make_cfg<3, 1, 16>(),
+      env_i64("DBB_K1_WPI4", 8) >= 8 ? make_cfg<4, 8, 6>() : env_i64("DBB_K1_WPI4", 8) >= 4 ? make_cfg<4, 4, 6>() : make_cfg<4, 2, 6>()};
+  return cfg[c];
+}
+
+// CTAs per SM of a class kernel on the current device (0: does not fit); DBB_K1_OCC<S> caps it (tuning switch)
+int class_occupancy(int c) {
+  const ClassCfg& k = class_cfg(c);
+  if (cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k.smem) != cudaSuccess) return 0;
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k.fn, k.threads, k.smem) != cudaSuccess) return 0;
+  static const int64_t cap[4] = {env_i64("DBB_K1_OCC1", 0), env_i64("DBB_K1_OCC2", 0), env_i64("DBB_K1_OCC3", 0), env_i64("DBB_K1_OCC4", 0)};
+  if (cap[c] > 0 && cap[c] < occ) occ = (int)cap[c];
+  return occ;
+}
+
 int launch_class(const dbb_count_plan* plan, int cls, const void* d_codes, const void* d_valid,
                  uint32_t* d_counts, float* d_freq, int64_t freq_stride, cudaStream_t st) {
-  const uint32_t n = plan->class_count[cls];
+  uint32_t n = plan->class_count[cls];
   if (n == 0) return DBB_OK;
-  const size_t smem = (size_t)(256 + Geo<S>::WORDS + 160 + WPI * 16) * sizeof(uint32_t);
-  auto kern = count_kernel<S, WPI, MINB>;
-  DBB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int occ = 0;
-  DBB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * WPI, smem));
-  if (occ < 1) { dbb::set_error("count kernel S=%d does not fit on the device", S); return DBB_ERR_CUDA; }
-  // DBB_K1_OCC<S> caps the CTAs per SM of a class (tuning switch; 0 = the occupancy limit)
-  static const int64_t cap = env_i64(S == 1 ? "DBB_K1_OCC1" : S == 2 ? "DBB_K1_OCC2" : S == 3 ? "DBB_K1_OCC3" : "DBB_K1_OCC4", 0);
-  if (cap > 0 && cap < occ) occ = (int)cap;
-  const uint32_t grid = (uint32_t)std::min<int64_t>((int64_t)occ * plan->sm_count, (int64_t)n);
-  kern<<<grid, 32 * WPI, smem, st>>>(plan->d_items + plan->class_begin[cls], n, (const uint4*)d_codes,
-                                       (const uint64_t*)d_valid, d_counts, d_freq, freq_stride, plan->d_split_counts);
-  DBB_CUDA_TRY(cudaGetLastError());
+  const ClassCfg& k = class_cfg(cls);
+  const Item* items = plan->d_items + plan->class_begin[cls];
+  const uint4* codes = (const uint4*)d_codes;
+  const uint64_t* valid = (const uint64_t*)d_valid;
+  uint32_t* split_counts = plan->d_split_counts;
+  void* args[] = {&items, &n, &codes, &valid, &d_counts, &d_freq, &freq_stride, &split_counts};
+  DBB_CUDA_TRY(cudaLaunchKernel(k.fn, dim3(plan->class_grid[cls]), dim3(k.threads), args, k.smem, st));
   return DBB_OK;
 }
 
@@ -527,6 +548,12 @@ int count_plan_rebuild(dbb_count_plan* plan, const int64_t* h_blk_off, int64_t n
   plan->h_items.reserve((size_t)n_seq + 16);
   for (int c = 0; c < 4; ++c) {
     std::stable_sort(cls[c].begin(), cls[c].end(), [](const Item& a, const Item& b) { return a.n_blocks > b.n_blocks; });
+    plan->class_grid[c] = 0;
+    if (!cls[c].empty()) {
+      const int occ = class_occupancy(c);
+      if (occ < 1) { dbb::set_error("count kernel S=%d does not fit on the device", c + 1); return DBB_ERR_CUDA; }
+      plan->class_grid[c] = (uint32_t)std::min<int64_t>((int64_t)occ * plan->sm_count, (int64_t)cls[c].size());
+    }
     plan->class_begin[c] = (uint32_t)plan->h_items.size();
     plan->class_count[c] = (uint32_t)cls[c].size();
     plan->h_items.insert(plan->h_items.end(), cls[c].begin(), cls[c].end());
@@ -630,17 +657,7 @@ DBB_EXPORT int dbb_tetra_count_dev(dbb_count_plan* plan, const void* d_codes, co
     if (plan->class_count[c] == 0) continue;
     cudaStream_t cs = plan->class_stream[c];
     DBB_CUDA_TRY(cudaStreamWaitEvent(cs, plan->ev_fork, 0));
-    // warps per item (= per CTA) and ring depth: env overrides exist for tuning sweeps (profiles/), the defaults are
-    // the measured best
-    static const int w2 = (int)env_i64("DBB_K1_WPI2", 2), w3 = (int)env_i64("DBB_K1_WPI3", 2), w4 = (int)env_i64("DBB_K1_WPI4", 8);
-#define DBB_LAUNCH(S_, W_, B_) rc = launch_class<S_, W_, B_>(plan, c, d_codes, d_valid, d_counts, d_freq, freq_stride, cs)
-    switch (c) {
-      case 3: if (w4 >= 8) DBB_LAUNCH(4, 8, 6); else if (w4 >= 4) DBB_LAUNCH(4, 4, 6); else DBB_LAUNCH(4, 2, 6); break;
-      case 2: if (w3 >= 4) DBB_LAUNCH(3, 4, 8); else if (w3 >= 2) DBB_LAUNCH(3, 2, 12); else DBB_LAUNCH(3, 1, 16); break;
-      case 1: if (w2 >= 2) DBB_LAUNCH(2, 2, 12); else DBB_LAUNCH(2, 1, 16); break;
-      default: DBB_LAUNCH(1, 1, 16); break;
-    }
-#undef DBB_LAUNCH
+    rc = launch_class(plan, c, d_codes, d_valid, d_counts, d_freq, freq_stride, cs);
     if (rc != DBB_OK) return rc;
     DBB_CUDA_TRY(cudaEventRecord(plan->ev_join[c], cs));
     DBB_CUDA_TRY(cudaStreamWaitEvent(st, plan->ev_join[c], 0));

@@ -160,8 +160,9 @@ int upload_weights(KnnState& K, cudaStream_t st) {
 }
 
 int split_for(int64_t n_act, int64_t target) {
-  // ~5 work items per SM: the lists differ in length by an order of magnitude, whole row tiles do not balance, but every
-  // extra segment refills its own top-k lists
+  // ~20 work items per SM (at most 8 segments per row tile): the lists differ in length by an order of magnitude, whole
+  // row tiles do not balance.  Every segment fills its own top-k lists, but the segments of a row tile share the k-th best
+  // distance they have proven so far (Params::gthr in pairs.cu), so a later segment starts with a tight threshold
   return (int)std::min<int64_t>(8, std::max<int64_t>(1, (target + std::max<int64_t>(n_act, 1) - 1) / std::max<int64_t>(n_act, 1)));
 }
 
@@ -228,7 +229,7 @@ DBB_EXPORT int dbb_knn_dev(dbb_ctx* ctx_in, const dbb_pairs_input* in, const dbb
   DBB_CUDA_TRY(cudaGetDevice(&dev));
   DBB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   static const int64_t items_target_env = [] { const char* e = getenv("DBB_PRUNE_ITEMS"); return (e && *e) ? atoll(e) : 0ll; }();
-  const int64_t items_target = items_target_env > 0 ? items_target_env : 5ll * sms;
+  const int64_t items_target = items_target_env > 0 ? items_target_env : 20ll * sms;
 
   // ---- buffers (grow-only, kept in the context between calls)
   if (!K.h_info) DBB_CUDA_TRY(cudaMallocHost((void**)&K.h_info, 8 * sizeof(int64_t)));
@@ -292,11 +293,11 @@ DBB_EXPORT int dbb_knn_dev(dbb_ctx* ctx_in, const dbb_pairs_input* in, const dbb
   d.sig = pb.sig_sorted; d.length = pb.length; d.td_bound = pb.td_bound; d.gc = pb.gc; d.gc_mbin = pb.gc_mbin; d.gc_lbin = pb.gc_lbin;
   d.cov = pb.cov; d.cov_lbin = pb.cov_lbin;
   d.col_id = pb.col_id; d.item_order = pb.item_order; d.tile_off = pb.tile_off; d.tile_list = pb.tile_list;
-  // Work items: every row tile in split_for(...) strided segments (~5 items per SM).  The sweep ends with its longest
-  // item (C2: 782 items, the last CTA finishing 10 % after the mean), but cutting the long lists more finely
-  // (dbb_pairs_input.split_tiles; DBB_PRUNE_SEG_TILES=<tiles per segment> to try it) costs more than it evens out: every
-  // segment re-converges its own top-k thresholds (C2: 24 / 45 / 96 tiles per segment -> 14.7 / 13.6 / 13.5 ms against
-  // 12.2 ms for the uniform split, profiles/r02_k2_notes.md).
+  // Work items: every row tile in split_for(...) strided segments.  The sweep ends with its longest item; since the
+  // segments of a row tile share their proven k-th best distances, finer cuts are nearly free (C2, 391 row tiles: 2 / 4 /
+  // 8 segments -> 11.0 / 10.8 / 10.7 ms, CTA finish times max / mean 1.05 / 1.03 / 1.01; without the shared bound 2
+  // segments took 12.2 ms and finer cuts were slower, profiles/r02_k2_notes.md).  DBB_PRUNE_SEG_TILES=<tiles per segment>
+  // selects the length-adaptive cut (dbb_pairs_input.split_tiles) instead.
   static const int64_t seg_env = [] { const char* e = getenv("DBB_PRUNE_SEG_TILES"); return (e && *e) ? atoll(e) : 0ll; }();
   if (seg_env <= 0) { d.split_all = split_for(n_mine, items_target); d.split_tiles = 0; }
   else { d.split_all = 8; d.split_tiles = (int32_t)std::min<int64_t>(seg_env, 1 << 30); }

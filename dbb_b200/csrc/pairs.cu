@@ -87,6 +87,8 @@ struct Params {
   // split into n_seg column segments (separate items) whose partial results are merged afterwards
   int32_t n_full_rt, n_seg, n_items, debug_skip_epilogue;
   int32_t seg_tiles;        // > 0: a tile list of L entries uses min(n_seg, ceil(L / seg_tiles)) of its n_seg segment slots
+  float* gthr;              // [split row tiles][TILE] k-th best distance of a row SHARED by the segments of its row tile
+                            // (an upper bound of the final k-th best: any full segment list proves one), or nullptr
   int32_t opaque_zero;         // always 0 (see the k4 loop)
   uint32_t* item_counter;
   unsigned long long* stats;   // profiling builds only (-DDBB_K2_STATS, run with DBB_K2_STATS=1): [0] queued pairs, [1] drains, [2] top-k candidates
@@ -293,7 +295,7 @@ __device__ __noinline__ void process_row_pair(const Params& P, int par, int warp
         if (cd <= sm.thr[crow]) {            // the list may have tightened since the ballot
           const int32_t cc = (int32_t)(col_base + (src & 15) + 16 * j);
           const float nt = list_insert(sm, crow, cd, cc, k, lane, P.col_id);
-          if (lane == 0) sm.thr[crow] = nt;
+          if (lane == 0) sm.thr[crow] = fminf(nt, sm.thr[crow]);     // (a shared bound may already be tighter than this list)
         }
         __syncwarp();
       }
@@ -446,7 +448,7 @@ __device__ __noinline__ void drain_queue(const Params& P, int par, int warp, int
         const int32_t cc = (int32_t)__shfl_sync(0xffffffffu, (int)cj, src);
         if (cd <= sm.thr[crow]) {          // the list may have tightened since the candidate was flagged
           const float nt = list_insert(sm, crow, cd, cc, k, lane, P.col_id);
-          if (lane == 0) sm.thr[crow] = nt;
+          if (lane == 0) sm.thr[crow] = fminf(nt, sm.thr[crow]);     // (a shared bound may already be tighter than this list)
         }
         __syncwarp();
       }
@@ -489,7 +491,7 @@ __device__ __noinline__ void test_row_pair(int par, int warp, int lane, int i, i
     float tau = m == 1 ? m1 : (m == 2 ? m2 : m3);
     #pragma unroll
     for (int o = 1; o < 16; o <<= 1) tau = fmaxf(tau, __shfl_xor_sync(0xffffffffu, tau, o));
-    thr_i = tau;
+    thr_i = fminf(tau, thr_i);               // (the row's shared bound, if another segment already has one)
   }
   // row-side bound: the row's TD bound or its current k-th best, whichever is larger; column side: the column's
   // TD bound (-inf beyond the last column, see issue_chunk)
@@ -632,10 +634,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pairs_kernel(const __grid_const
     // work position -> row tile, segment of its tile sequence [t0, t1)
     int pos = item, seg = -1, srt = 0;
     if (item >= P.n_full_rt) {
+      // segment-major: segment 0 of every split row tile, then segment 1 of every one, ... -- when a later segment of a
+      // row tile starts, its earlier ones have (mostly) finished and left their k-th best distances in gthr
       const int t = item - P.n_full_rt;
-      srt = t / P.n_seg;                   // index among the split row tiles (slot of the partial results)
+      const int n_split = (P.n_items - P.n_full_rt) / P.n_seg;
+      seg = t / n_split;
+      srt = t % n_split;                   // index among the split row tiles (slot of the partial results)
       pos = P.n_full_rt + srt;
-      seg = t % P.n_seg;
     }
     const int rt = P.item_order ? __ldg(P.item_order + pos) : pos;
     const int64_t list_base = P.tile_off ? __ldg(P.tile_off + rt) : 0;
@@ -693,7 +698,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pairs_kernel(const __grid_const
       sm.rows[lr] = rs;
       sm.cnt[lr] = 0;
       sm.bp_lo[lr] = 0u; sm.bp_hi[lr] = 0u;
-      sm.thr[lr] = F_TOPK ? INFINITY : -INFINITY;
+      sm.thr[lr] = F_TOPK ? ((P.gthr && seg >= 0) ? __ldcg(P.gthr + (int64_t)srt * TILE + lr) : INFINITY) : -INFINITY;
     }
     for (int r = 0; r < RW; ++r) {
       sm.list_d[warp * RW + r][lane] = INFINITY;
@@ -819,6 +824,19 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pairs_kernel(const __grid_const
         if (qn && P.debug_skip_epilogue != 2) drain_queue<FLAGS, WARPS>(P, ts & 1, warp, lane, qn, row_base, col_base);
       }
       DBB_LAP(t_drain)
+      if (F_TOPK && P.gthr && seg >= 0) {
+        // exchange with the other segments of this row tile: publish this list's k-th best (once it has one) and pick
+        // up the smallest one published so far -- every full list proves an upper bound of the row's final k-th best,
+        // so candidates above it cannot be in the merged top-k (ties pass: the tests are <=)
+        __syncwarp();
+        if (lane < RW) {
+          const int lr = warp * RW + lane;
+          const float loc = sm.thr[lr];
+          const unsigned int old = atomicMin(reinterpret_cast<unsigned int*>(P.gthr + (int64_t)srt * TILE + lr), __float_as_uint(loc));
+          sm.thr[lr] = fminf(loc, __uint_as_float(old));
+        }
+        __syncwarp();
+      }
     }  // column tiles
 #ifdef DBB_K2_STATS
     if (P.stats && lane == 0) {
@@ -989,7 +1007,7 @@ DBB_EXPORT int64_t dbb_pairs_scratch_bytes(int64_t n, int64_t rows, int32_t k) {
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int64_t n_full, rem; int n_seg;
   plan_items((rows + TILE - 1) / TILE, (n + TILE - 1) / TILE, sms, &n_full, &rem, &n_seg);
-  return 256 + rem * TILE * n_seg * ((int64_t)std::max(k, 1) * 8 + 16);
+  return 8192 + rem * TILE * n_seg * ((int64_t)std::max(k, 1) * 8 + 16) + rem * TILE * 4;
 }
 
 DBB_EXPORT int dbb_pairs_launches(int64_t n, int64_t rows) {
@@ -1075,7 +1093,9 @@ DBB_EXPORT int dbb_pairs_dev(const dbb_pairs_input* in, int64_t row0, int64_t ro
   off_dist = off_idx + (size_t)rem * TILE * n_seg * k_ * 4;
   off_cnt = off_dist + (size_t)rem * TILE * n_seg * k_ * 4;
   off_bp = (off_cnt + (size_t)rem * TILE * n_seg * 4 + 7) & ~(size_t)7;
-  total = off_bp + (size_t)rem * TILE * n_seg * 8;
+  const size_t off_gthr = off_bp + (size_t)rem * TILE * n_seg * 8;
+  const bool share_thr = rem > 0 && n_seg > 1 && out->k > 0;
+  total = off_gthr + (share_thr ? (size_t)rem * TILE * 4 : 0);
   // stream-ordered scratch; keep freed blocks cached in the device pool instead of returning them to the
   // driver at every synchronisation (the default release threshold is 0)
   static bool pool_configured[64] = {false};       // per device ordinal
@@ -1097,6 +1117,11 @@ DBB_EXPORT int dbb_pairs_dev(const dbb_pairs_input* in, int64_t row0, int64_t ro
   P.part_dist = (float*)(scratch + off_dist);
   P.part_cnt = (int32_t*)(scratch + off_cnt);
   P.part_bp = (int64_t*)(scratch + off_bp);
+  P.gthr = nullptr;
+  if (share_thr) {
+    P.gthr = (float*)(scratch + off_gthr);
+    DBB_CUDA_TRY(cudaMemsetAsync(P.gthr, 0x7f, (size_t)rem * TILE * 4, st));      // 0x7f7f7f7f = 3.4e38: "no bound yet"
+  }
 
   const unsigned grid = (unsigned)std::min<int64_t>(P.n_items, sms);
   int flags = (in->td_bound ? 1 : 0) | ((in->gc || in->cov) ? 2 : 0) | (masks ? 4 : 0) | (out->k > 0 ? 8 : 0);
