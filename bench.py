@@ -440,6 +440,11 @@ def run_ours(args):
         torch.cuda.synchronize(); barrier()
         e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
         e2e_count_s = max_over_ranks(tc / e2e_steps)
+        # how the last stage-1 call moved its input: ASCII by the copy engine / planes packed by host threads
+        import ctypes
+        up_ascii, up_planes, up_thr = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int32(0)
+        e2e_count()
+        _lib.check(L.dbb_host_upload_stats(ctypes.byref(up_ascii), ctypes.byref(up_planes), ctypes.byref(up_thr)))
         # the same stage-1 call with PAGEABLE numpy buffers (what GenomicSignatures.signatures hands over): the library
         # stages them through its own pinned ring (csrc/host_api.cu::h2d_any)
         a_page = np.array(a_np)
@@ -463,7 +468,8 @@ def run_ours(args):
         h2d_ceiling_gbs = float(total_bp) * 3 / max_over_ranks(time.perf_counter() - t1) / 1e9
         del d_tmp
         rows = r1 - r0
-        h2d = int(a_np.nbytes + seq_off.nbytes * 2 + (n_total * 136 * 4 + n_total * 8 if world == 1 else my_n * 136 * 4))
+        # bytes that crossed the link per step (stage 1: ASCII route + packed route + offsets; stage 2: signatures + tables)
+        h2d = int(up_ascii.value + up_planes.value + seq_off.nbytes * 2 + (n_total * 136 * 4 + n_total * 8 if world == 1 else my_n * 136 * 4))
         d2h = int(my_n * 136 * 8 + rows * (K_NN * 8 + 12))
 
     # ---------------- parity spot check (untimed): sampled scaffolds / rows against the oracle ----------
@@ -573,6 +579,10 @@ def run_ours(args):
                 'value_pageable_host_buffers': total_bp / e2e_page_s / 1e9, 'h2d_concurrent_ceiling_gbs': h2d_ceiling_gbs,
                 'frac_of_h2d_ceiling': (total_bp / e2e_count_s / 1e9) / h2d_ceiling_gbs, 'pipeline_gbp_per_s': total_bp / e2e_s / 1e9, 'pipeline_pairs_per_s': pairs_total / e2e_s,
                 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                'host_input_bytes_per_step': int(a_np.nbytes),
+                'upload': {'ascii_route_bytes': int(up_ascii.value), 'host_packed_route_bytes': int(up_planes.value),
+                           'host_pack_threads': int(up_thr.value),
+                           'note': 'dbb_tetra_signatures_host sends part of every batch as ASCII (copy engine) and part as planes packed by host threads (0.375 B/base); rank 0 values'},
                 'api': 'dbb_tetra_signatures_host + dbb_pairs_host (pinned host buffers)' if args.no_prune else
                        'dbb_tetra_signatures_host + dbb_knn_host (pinned host buffers)' if world == 1 else 'dbb_tetra_signatures_host (pinned host buffers) + H2D of the signatures, all-gather, dbb_knn_dev, D2H of the results'},
         'pruning': pruning,

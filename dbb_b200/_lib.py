@@ -102,6 +102,7 @@ SIGNATURES = {
     'dbb_packed_blocks': (c_i64, [c_i64]),
     'dbb_block_offsets': (ctypes.c_int, [c_vp, c_i64, c_vp]),
     'dbb_pack_ascii_dev': (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp]),
+    'dbb_pack_ascii_host': (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),
     'dbb_pack_ranges_dev': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]),
     'dbb_split_scaffolds_dev': (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'dbb_base_count_dev': (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),
@@ -111,6 +112,7 @@ SIGNATURES = {
     'dbb_count_class_limits': (ctypes.c_int, [c_vp]),
     'dbb_tetra_count_dev': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
     'dbb_tetra_signatures_host': (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
+    'dbb_host_upload_stats': (ctypes.c_int, [c_vp, c_vp, c_vp]),
     'dbb_pairs_dev': (ctypes.c_int, [ctypes.POINTER(PairsInput), c_i64, c_i64, ctypes.POINTER(PairsOutput), c_vp]),
     'dbb_pairs_scratch_bytes': (c_i64, [c_i64, c_i64, c_i32]),
     'dbb_pairs_launches': (ctypes.c_int, [c_i64, c_i64]),

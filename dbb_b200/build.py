@@ -12,9 +12,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OBJ = os.path.join(CSRC, '_obj')
 LIB = os.path.join(HERE, 'libdbbcuda.so')
-SOURCES = ['table.cu', 'pack.cu', 'count.cu', 'pairs.cu', 'refine.cu', 'prune.cu', 'knn.cu', 'greedy.cu', 'pca.cu', 'split.cu', 'synth.cu', 'host_api.cu']
+SOURCES = ['table.cu', 'pack.cu', 'count.cu', 'pairs.cu', 'refine.cu', 'prune.cu', 'knn.cu', 'greedy.cu', 'pca.cu', 'split.cu', 'synth.cu', 'host_api.cu',
+           'hostpack.cpp']          # (.cpp: host-only code with x86 target attributes, compiled by g++ directly)
 HEADERS = [os.path.join(CSRC, 'common.cuh'), os.path.join(HERE, '..', 'include', 'dbb_cuda.h')]
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+CXX = os.environ.get('CXX', 'g++')
+CXXFLAGS = ['-O3', '-std=c++17', '-fPIC', '-fvisibility=hidden', '-Wall']
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
          '-Xcompiler', '-fPIC,-fvisibility=hidden,-ffp-contract=off', '--expt-relaxed-constexpr']
 
@@ -27,14 +30,17 @@ def _stale(target, deps):
 
 
 def _compile(src, verbose):
-    obj = os.path.join(OBJ, src.replace('.cu', '.o'))
+    obj = os.path.join(OBJ, os.path.splitext(src)[0] + '.o')
     path = os.path.join(CSRC, src)
     if not _stale(obj, [path] + HEADERS):
         return obj, ''
-    cmd = [NVCC] + FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', path, '-o', obj]
+    if src.endswith('.cpp'):
+        cmd = [CXX] + CXXFLAGS + ['-c', path, '-o', obj]
+    else:
+        cmd = [NVCC] + FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', path, '-o', obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError('nvcc failed for %s:\n%s\n%s' % (src, r.stdout, r.stderr))
+        raise RuntimeError('compiler failed for %s:\n%s\n%s' % (src, r.stdout, r.stderr))
     return obj, r.stderr
 
 

@@ -6,6 +6,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -26,8 +29,74 @@ void DevBuf::release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 constexpr size_t PIN_CHUNK = 4u << 20;   // staging ring for pageable input: 8 chunks of 4 MB per lane
 constexpr int PIN_SLOTS = 8;
 
+void host_pack_sequence(const uint8_t* seq, int64_t len, uint32_t* codes, uint64_t* valid);     // hostpack.cpp
+
+struct PinBuf {          // grow-only pinned host buffer
+  uint8_t* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return DBB_OK;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    const size_t want = bytes + bytes / 8;
+    cudaError_t e = cudaHostAlloc((void**)&p, want, cudaHostAllocDefault);
+    if (e != cudaSuccess) { set_error("cudaHostAlloc(%zu) failed: %s", want, cudaGetErrorString(e)); p = nullptr; return DBB_ERR_NOMEM; }
+    cap = want;
+    return DBB_OK;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+// A few persistent host threads (the packers of submit_batch).  start() hands every thread the same job, wait() returns
+// when all of them are back.
+struct HostPool {
+  std::vector<std::thread> th;
+  std::mutex m;
+  std::condition_variable cv, cv_done;
+  std::function<void(int)> job;
+  uint64_t gen = 0;
+  int running = 0;
+  bool stop = false;
+  explicit HostPool(int n) {
+    for (int t = 0; t < n; ++t) th.emplace_back([this, t] {
+      uint64_t seen = 0;
+      for (;;) {
+        std::function<void(int)> j;
+        {
+          std::unique_lock<std::mutex> lk(m);
+          cv.wait(lk, [&] { return stop || gen != seen; });
+          if (stop) return;
+          seen = gen;
+          j = job;
+        }
+        j(t);
+        { std::lock_guard<std::mutex> lk(m); if (--running == 0) cv_done.notify_all(); }
+      }
+    });
+  }
+  void start(std::function<void(int)> j) {
+    std::lock_guard<std::mutex> lk(m);
+    job = std::move(j); running = (int)th.size(); ++gen;
+    cv.notify_all();
+  }
+  void wait() { std::unique_lock<std::mutex> lk(m); cv_done.wait(lk, [&] { return running == 0; }); }
+  ~HostPool() {
+    { std::lock_guard<std::mutex> lk(m); stop = true; }
+    cv.notify_all();
+    for (auto& t : th) t.join();
+  }
+};
+
+constexpr int DMA_DEPTH = 3;             // ASCII copies in flight on the copy engine
+
 struct Lane {            // one in-flight batch of stage 1
   cudaStream_t st = nullptr;
+  cudaStream_t st2 = nullptr;           // copies of the host-packed planes (runs beside the ASCII copies of st)
+  cudaEvent_t ev2 = nullptr, dma_ev[DMA_DEPTH] = {nullptr, nullptr, nullptr};
+  PinBuf pk_codes, pk_valid;            // host-packed planes of the batch, same geometry as codes / valid
+  std::vector<int64_t> unit;            // scaffold boundaries of the ~1 MB work units of the batch
+  std::unique_ptr<std::atomic<uint8_t>[]> unit_done;
+  size_t unit_cap = 0;
   DevBuf ascii, seq_off, blk_off, codes, valid, counts, freq;
   uint8_t* pin = nullptr;               // pinned ring (lazily allocated, only when a caller passes pageable memory)
   cudaEvent_t pin_ev[PIN_SLOTS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -35,7 +104,12 @@ struct Lane {            // one in-flight batch of stage 1
   int64_t s0 = 0, s1 = 0;
   std::vector<int64_t> h_off, h_blk;
 };
-struct SigState { Lane lanes[2]; };
+struct SigState {
+  Lane lanes[2];
+  HostPool* pool = nullptr;
+  int pool_threads = -1;
+  int64_t ascii_bytes = 0, plane_bytes = 0;      // what the last dbb_tetra_signatures_host call sent up by either route
+};
 struct PairsHostState {
   DevBuf dense, sig, len, tdb, gc, gcm, gcl, gclo, gchi, cov, covl, covlo, covhi;
   DevBuf o_idx, o_dist, o_cnt, o_bp, o_td, o_gc, o_cov;
@@ -48,8 +122,13 @@ void free_sig_state(SigState* s) {
     if (L.plan) dbb_count_plan_destroy(L.plan);
     if (L.pin) cudaFreeHost(L.pin);
     for (auto& e : L.pin_ev) if (e) cudaEventDestroy(e);
+    L.pk_codes.release(); L.pk_valid.release();
+    for (auto& e : L.dma_ev) if (e) cudaEventDestroy(e);
+    if (L.ev2) cudaEventDestroy(L.ev2);
+    if (L.st2) cudaStreamDestroy(L.st2);
     if (L.st) cudaStreamDestroy(L.st);
   }
+  delete s->pool;
   delete s;
 }
 void free_pairs_state(PairsHostState* s) {
@@ -135,7 +214,10 @@ DBB_EXPORT int dbb_ctx_destroy(dbb_ctx* ctx) {
 namespace {
 
 using dbb::DevBuf;
+using dbb::DMA_DEPTH;
+using dbb::HostPool;
 using dbb::Lane;
+using dbb::SigState;
 using dbb::PIN_CHUNK;
 using dbb::PIN_SLOTS;
 
@@ -204,7 +286,142 @@ int h2d_any(Lane& L, int device, void* dst, const uint8_t* src, size_t nbytes) {
   return DBB_OK;
 }
 
-int submit_batch(Lane& L, int device, const uint8_t* ascii, const int64_t* seq_off, int64_t s0, int64_t s1,
+// Packer threads of dbb_tetra_signatures_host: DBB_HOST_PACK_THREADS, else the hardware threads this process can count on
+// (all of them divided by LOCAL_WORLD_SIZE when a launcher started one process per GPU) minus one for the caller,
+// at most 16.  0 switches the host packing off.
+int pack_threads() {
+  static const int n = [] {
+    const char* e = getenv("DBB_HOST_PACK_THREADS");
+    if (e && *e) return std::max(0, std::min(atoi(e), 64));
+    const char* m = getenv("DBB_HOST_PACK");
+    if (m && *m == '0') return 0;
+    int hw = (int)std::thread::hardware_concurrency();
+    const char* lw = getenv("LOCAL_WORLD_SIZE");
+    const int ranks = (lw && atoi(lw) > 0) ? atoi(lw) : 1;
+    return std::max(0, std::min(hw / ranks - 1, 16));
+  }();
+  return n;
+}
+
+constexpr int64_t UNIT_BYTES = 1 << 20;        // work unit of the hybrid upload
+constexpr int64_t HYBRID_MIN_BYTES = 8 << 20;  // smaller batches go up as ASCII in one copy
+
+// Upload of one batch by BOTH routes at once.  The batch is cut into units of whole scaffolds (~1 MB of ASCII).  The
+// calling thread feeds the copy engine with ASCII units from the FRONT of the batch, DMA_DEPTH copies in flight, so it
+// claims units exactly as fast as the link moves them; the packer threads claim units from the BACK, pack them into the
+// pinned planes (0.375 bytes per base) and the calling thread sends finished runs of them up on a second stream.  When
+// the two fronts meet the batch is up: scaffolds [0, *n_ascii) arrived as ASCII (the pack kernel handles them), the rest
+// as planes.
+// Used for PAGEABLE input (numpy arrays, Python bytes: what GenomicSignatures.signatures hands over), where the ASCII
+// route is the driver's staged copy (~10 GB/s): C2 from pageable buffers 30.8 -> 43.6 Gbp/s with 15 packer threads
+// (the pinned ring of h2d_any, which this replaces for large batches, copies every byte twice on the host).  PINNED
+// input goes up as ASCII in one copy: measured on the same box, the mixed upload only moves the split (4 / 8 / 16
+// packers carry 33 / 48 / 60 % of the bases) while the sum of the two routes stays at ~50 GB/s of input read from host
+// memory, i.e. 49-50 Gbp/s against 51.7 for the plain copy -- the pinned line is bound by reading the input once, not
+// by the bytes on the link.  DBB_HOST_PACK=0: ASCII only; =all: packers only; =hybrid: mixed upload for pinned input too.
+int hybrid_upload(Lane& L, SigState& S, int device, const uint8_t* base, int64_t ns, int64_t nbytes, int64_t* n_ascii) {
+  *n_ascii = ns;
+  const int n_thr = pack_threads();
+  static const int mode = [] {
+    const char* m = getenv("DBB_HOST_PACK");
+    return !m ? 0 : strcmp(m, "all") == 0 ? 2 : strcmp(m, "hybrid") == 0 ? 1 : 0;
+  }();
+  const bool pack_all = mode == 2;
+  cudaPointerAttributes attr;
+  const bool pageable = cudaPointerGetAttributes(&attr, base) != cudaSuccess || attr.type == cudaMemoryTypeUnregistered;
+  cudaGetLastError();                                        // (an unknown host pointer is reported as an error on old drivers)
+  if (n_thr <= 0 || (!pack_all && nbytes < HYBRID_MIN_BYTES) || (!pageable && mode == 0))
+    return h2d_any(L, device, L.ascii.p, base, (size_t)nbytes);
+  if (!S.pool || S.pool_threads != n_thr) { delete S.pool; S.pool = new HostPool(n_thr); S.pool_threads = n_thr; }
+  if (!L.st2) {
+    DBB_CUDA_TRY(cudaStreamCreateWithFlags(&L.st2, cudaStreamNonBlocking));
+    DBB_CUDA_TRY(cudaEventCreateWithFlags(&L.ev2, cudaEventDisableTiming));
+    for (auto& e : L.dma_ev) DBB_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  const int64_t nblk = L.h_blk[ns];
+  DBB_TRY(L.pk_codes.reserve((size_t)std::max<int64_t>(nblk, 1) * 16));
+  DBB_TRY(L.pk_valid.reserve((size_t)std::max<int64_t>(nblk, 1) * 8));
+  // units
+  L.unit.clear();
+  L.unit.push_back(0);
+  for (int64_t s = 0, acc0 = 0; s < ns; ++s) {
+    if (L.h_off[s + 1] - acc0 >= UNIT_BYTES || s + 1 == ns) { L.unit.push_back(s + 1); acc0 = L.h_off[s + 1]; }
+  }
+  const int64_t U = (int64_t)L.unit.size() - 1;
+  if ((size_t)U > L.unit_cap) { L.unit_cap = (size_t)U + 64; L.unit_done.reset(new std::atomic<uint8_t>[L.unit_cap]); }
+  for (int64_t u = 0; u < U; ++u) L.unit_done[u].store(0, std::memory_order_relaxed);
+
+  std::mutex mu;
+  int64_t front = 0, back = U - 1;               // units [front, back] are unclaimed
+  const int64_t* h_off = L.h_off.data();
+  const int64_t* h_blk = L.h_blk.data();
+  const int64_t* unit = L.unit.data();
+  std::atomic<uint8_t>* done = L.unit_done.get();
+  uint8_t* pkc = L.pk_codes.p;
+  uint8_t* pkv = L.pk_valid.p;
+  S.pool->start([&, h_off, h_blk, unit, done, pkc, pkv, base](int) {
+    for (;;) {
+      int64_t u;
+      { std::lock_guard<std::mutex> lk(mu); if (front > back) return; u = back--; }
+      for (int64_t s = unit[u]; s < unit[u + 1]; ++s)
+        dbb::host_pack_sequence(base + h_off[s], h_off[s + 1] - h_off[s], reinterpret_cast<uint32_t*>(pkc + 16 * h_blk[s]),
+                                reinterpret_cast<uint64_t*>(pkv + 8 * h_blk[s]));
+      done[u].store(1, std::memory_order_release);
+    }
+  });
+
+  cudaError_t e = cudaSuccess;
+  int64_t issued_hi = U;                          // packed units [issued_hi, U) are on their way
+  int inflight = 0, ev_head = 0;                  // ASCII copies in flight: events ev_head .. ev_head + inflight - 1 (mod DEPTH)
+  bool all_claimed = false;
+  int64_t boundary = -1;                          // first packer-claimed unit, known once everything is claimed
+  while (e == cudaSuccess) {
+    bool progress = false;
+    // packed route: the run of finished units just below issued_hi
+    int64_t lo = issued_hi;
+    while (lo > 0 && done[lo - 1].load(std::memory_order_acquire)) --lo;
+    if (lo < issued_hi && (issued_hi - lo >= 4 || all_claimed)) {
+      const int64_t b0 = h_blk[unit[lo]], b1 = h_blk[unit[issued_hi]];
+      if (b1 > b0) {
+        e = cudaMemcpyAsync((uint8_t*)L.codes.p + 16 * b0, pkc + 16 * b0, (size_t)(b1 - b0) * 16, cudaMemcpyHostToDevice, L.st2);
+        if (e == cudaSuccess) e = cudaMemcpyAsync((uint8_t*)L.valid.p + 8 * b0, pkv + 8 * b0, (size_t)(b1 - b0) * 8, cudaMemcpyHostToDevice, L.st2);
+      }
+      issued_hi = lo;
+      progress = true;
+    }
+    // ASCII route: retire finished copies, claim the next units while the engine has room
+    while (inflight > 0 && cudaEventQuery(L.dma_ev[ev_head]) == cudaSuccess) { ev_head = (ev_head + 1) % DMA_DEPTH; --inflight; progress = true; }
+    if (!all_claimed && !pack_all && inflight < DMA_DEPTH) {
+      int64_t u0 = -1, u1 = -1;
+      { std::lock_guard<std::mutex> lk(mu); if (front <= back) { u0 = front; u1 = std::min(front + 2, back + 1); front = u1; } }
+      if (u0 >= 0) {
+        const int64_t o0 = h_off[unit[u0]], o1 = h_off[unit[u1]];
+        if (o1 > o0) e = cudaMemcpyAsync((uint8_t*)L.ascii.p + o0, base + o0, (size_t)(o1 - o0), cudaMemcpyHostToDevice, L.st);
+        const int slot = (ev_head + inflight) % DMA_DEPTH;
+        if (e == cudaSuccess) e = cudaEventRecord(L.dma_ev[slot], L.st);
+        ++inflight;
+        progress = true;
+      }
+    }
+    if (!all_claimed) {
+      std::lock_guard<std::mutex> lk(mu);
+      if (front > back) { all_claimed = true; boundary = front; }
+    }
+    if (all_claimed && issued_hi <= boundary) break;
+    if (!progress) std::this_thread::yield();
+  }
+  if (e != cudaSuccess) { std::lock_guard<std::mutex> lk(mu); front = back + 1; }      // stop the packers
+  S.pool->wait();
+  if (e != cudaSuccess) { dbb::set_error("hybrid upload failed: %s", cudaGetErrorString(e)); return DBB_ERR_CUDA; }
+  *n_ascii = unit[boundary];
+  S.ascii_bytes -= nbytes - h_off[*n_ascii];                 // (the caller charged the whole batch to the ASCII route)
+  S.plane_bytes += (h_blk[ns] - h_blk[*n_ascii]) * 24;
+  DBB_CUDA_TRY(cudaEventRecord(L.ev2, L.st2));
+  DBB_CUDA_TRY(cudaStreamWaitEvent(L.st, L.ev2, 0));
+  return DBB_OK;
+}
+
+int submit_batch(Lane& L, SigState& S, int device, const uint8_t* ascii, const int64_t* seq_off, int64_t s0, int64_t s1,
                  bool want_counts, bool want_freq) {
   const int64_t ns = s1 - s0;
   const int64_t byte0 = seq_off[s0], nbytes = seq_off[s1] - byte0;
@@ -229,11 +446,14 @@ int submit_batch(Lane& L, int device, const uint8_t* ascii, const int64_t* seq_o
   if (want_freq) DBB_TRY(L.freq.reserve((size_t)ns * DBB_NUM_KMERS * 4));
   if (!L.plan) DBB_TRY(dbb_count_plan_create(L.h_blk.data(), ns, &L.plan));
   else DBB_TRY(dbb::count_plan_rebuild(L.plan, L.h_blk.data(), ns, L.st));
-  DBB_TRY(h2d_any(L, device, L.ascii.p, ascii + byte0, (size_t)nbytes));
   DBB_CUDA_TRY(cudaMemcpyAsync(L.seq_off.p, L.h_off.data(), (ns + 1) * 8, cudaMemcpyHostToDevice, L.st));
   DBB_CUDA_TRY(cudaMemcpyAsync(L.blk_off.p, L.h_blk.data(), (ns + 1) * 8, cudaMemcpyHostToDevice, L.st));
-  DBB_TRY(dbb_pack_ascii_dev((const uint8_t*)L.ascii.p, (const int64_t*)L.seq_off.p, (const int64_t*)L.blk_off.p, ns,
-                             nblk, L.codes.p, L.valid.p, L.st));
+  int64_t n_ascii = ns;                 // scaffolds [0, n_ascii) arrive as ASCII, the others as host-packed planes
+  S.ascii_bytes += nbytes;
+  DBB_TRY(hybrid_upload(L, S, device, ascii + byte0, ns, nbytes, &n_ascii));
+  if (n_ascii > 0)
+    DBB_TRY(dbb_pack_ascii_dev((const uint8_t*)L.ascii.p, (const int64_t*)L.seq_off.p, (const int64_t*)L.blk_off.p, n_ascii,
+                               L.h_blk[n_ascii], L.codes.p, L.valid.p, L.st));
   DBB_TRY(dbb_tetra_count_dev(L.plan, L.codes.p, L.valid.p, want_counts ? (uint32_t*)L.counts.p : nullptr,
                               want_freq ? (float*)L.freq.p : nullptr, DBB_NUM_KMERS, L.st));
   return DBB_OK;
@@ -266,6 +486,7 @@ DBB_EXPORT int dbb_tetra_signatures_host(const uint8_t* ascii, const int64_t* se
   dbb::CtxLock lock(ctx);
   if (!ctx->sig) ctx->sig = new dbb::SigState();
   Lane* lanes = ctx->sig->lanes;
+  ctx->sig->ascii_bytes = ctx->sig->plane_bytes = 0;
   const char* env = getenv("DBB_HOST_BATCH_MB");
   const int64_t batch_bytes = (env && *env ? atoll(env) : 256) << 20;
   for (int i = 0; i < 2; ++i) {
@@ -283,7 +504,7 @@ DBB_EXPORT int dbb_tetra_signatures_host(const uint8_t* ascii, const int64_t* se
     while (e < n_seq && (e == s || seq_off[e + 1] - b0 <= batch_bytes)) ++e;
     Lane& L = lanes[cur];
     if (pending[cur]) { rc = collect_batch(L, counts, freq); pending[cur] = false; if (rc != DBB_OK) break; }
-    rc = submit_batch(L, ctx->device, ascii, seq_off, s, e, counts != nullptr, freq != nullptr);
+    rc = submit_batch(L, *ctx->sig, ctx->device, ascii, seq_off, s, e, counts != nullptr, freq != nullptr);
     if (rc != DBB_OK) break;
     pending[cur] = true;
     cur ^= 1;
@@ -297,6 +518,17 @@ DBB_EXPORT int dbb_tetra_signatures_host(const uint8_t* ascii, const int64_t* se
     }
   }
   return rc;
+}
+
+DBB_EXPORT int dbb_host_upload_stats(int64_t* ascii_bytes, int64_t* plane_bytes, int32_t* pack_threads_out) {
+  dbb_ctx* ctx = nullptr;
+  int rc = dbb::ctx_resolve(nullptr, &ctx);
+  if (rc != DBB_OK) return rc;
+  dbb::CtxLock lock(ctx);
+  if (ascii_bytes) *ascii_bytes = ctx->sig ? ctx->sig->ascii_bytes : 0;
+  if (plane_bytes) *plane_bytes = ctx->sig ? ctx->sig->plane_bytes : 0;
+  if (pack_threads_out) *pack_threads_out = pack_threads();
+  return DBB_OK;
 }
 
 namespace {

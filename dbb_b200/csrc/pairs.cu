@@ -100,28 +100,48 @@ struct Params {
   const int32_t* col_id;       // [n] the caller's id of column j (tie-breaks and knn_idx use it instead of j)
 };
 
-struct SmemLayout {
-  alignas(128) float a[NKC][TILE][KCH];
-  alignas(128) float b[NSTAGE][TILE][KCH];
-  float list_d[TILE][LIST_K];
-  int32_t list_j[TILE][LIST_K];
-  float2 q[QTOTAL];                      // per-warp queue of pairs that may be a neighbour or a top-k candidate:
+// Shared memory of one CTA.  TROWS = rows of the CTA's row tile (128, or 64 for the two-CTAs-per-SM instance), NST = stages of
+// the B ring, QT = queue entries of the CTA.
+template <int TROWS, int NST, int QT>
+struct SmemLayoutT {
+  alignas(128) float a[NKC][TROWS][KCH];
+  alignas(128) float b[NST][TILE][KCH];
+  float list_d[TROWS][LIST_K];
+  int32_t list_j[TROWS][LIST_K];
+  float2 q[QT];                          // per-warp queue of pairs that may be a neighbour or a top-k candidate:
                                          //   .x = distance, .y = bits of (row within the warp's rows) << 7 | (column
                                          //   within the tile); the every-pair path uses the first 256 .x as scratch
-  RowScalars rows[TILE];
-  uint32_t bp_lo[TILE], bp_hi[TILE];     // neighbourhood base pairs per row (64-bit as two native 32-bit atomics)
-  int32_t cnt[TILE];                     // neighbourhood size per row
-  float thr[TILE];                       // current k-th best distance per row (+inf until k found)
+  RowScalars rows[TROWS];
+  uint32_t bp_lo[TROWS], bp_hi[TROWS];   // neighbourhood base pairs per row (64-bit as two native 32-bit atomics)
+  int32_t cnt[TROWS];                    // neighbourhood size per row
+  float thr[TROWS];                      // current k-th best distance per row (+inf until k found)
   int32_t qn[MAX_WARPS];                 // queue fill per warp
   ColScalars cols[2];                    // column scalars of the t-th visited tile live in cols[t & 1]
-  alignas(8) uint64_t full[NSTAGE];
-  uint64_t empty[NSTAGE];
+  alignas(8) uint64_t full[NST];
+  uint64_t empty[NST];
   uint64_t a_full;
   int32_t item;
 };
 
+// Instances of the kernel by warp count:
+//    8 warps: one CTA per SM, 128-row tiles, 8x8 register tiles, 5-stage B ring (a whole column tile in flight)
+//   16 warps: as above with 4x8 register tiles (-DDBB_K2_WARPS16)
+//    4 warps: TWO CTAs per SM, each with a 64-row tile (one half of a 128-row work item), 8x8 register tiles, 2-stage
+//             B ring.  The eight warps of the big CTA reach their epilogues together (the ring couples them), and the
+//             FP32 pipe idles meanwhile (30 % of the cycles of the pruned sweep on C2); two independent CTAs drift
+//             apart, so one warp of every sub-partition is mostly in the FADD2 loop.
+template <int WARPS> struct Cfg {
+  static constexpr int TROWS = WARPS == 4 ? 64 : TILE;
+  static constexpr int NST = WARPS == 4 ? 2 : NSTAGE;
+  static constexpr int PRE = WARPS == 4 ? 1 : PREFETCH;
+  static constexpr int QT = WARPS == 4 ? QTOTAL / 2 : QTOTAL;
+  static constexpr int MINB = WARPS == 4 ? 2 : 1;
+  using Smem = SmemLayoutT<TROWS, NST, QT>;
+};
+
 static_assert(NSTAGE <= NKC, "column-scalar double buffer needs NSTAGE <= NKC");
-static_assert(sizeof(SmemLayout) <= 232448, "SmemLayout exceeds the 227 KB per-CTA shared memory limit");
+static_assert(sizeof(Cfg<8>::Smem) <= 232448, "SmemLayout exceeds the 227 KB per-CTA shared memory limit");
+static_assert(2 * (sizeof(Cfg<4>::Smem) + 1024) <= 233472, "two 4-warp CTAs do not fit the 228 KB of an SM");
 
 // ---- mbarrier / TMA primitives ------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -183,9 +203,11 @@ __device__ __forceinline__ float2 absdiff_acc(float2 acc, float2 a, float2 b) {
 // (instead of taking a reference parameter) so that the compiler keeps the shared address space: a generic
 // reference costs LD + QSPC-guarded atomics in the out-of-line slow paths.
 extern __shared__ __align__(128) uint8_t smem_raw[];
-__device__ __forceinline__ SmemLayout& smem() { return *reinterpret_cast<SmemLayout*>(smem_raw); }
+template <int WARPS>
+__device__ __forceinline__ typename Cfg<WARPS>::Smem& smem() { return *reinterpret_cast<typename Cfg<WARPS>::Smem*>(smem_raw); }
 
-__device__ __forceinline__ void add_bp(SmemLayout& sm, int lr, uint32_t v) {
+template <typename SM>
+__device__ __forceinline__ void add_bp(SM& sm, int lr, uint32_t v) {
   const uint32_t old = atomicAdd(&sm.bp_lo[lr], v);
   if (old + v < old) atomicAdd(&sm.bp_hi[lr], 1u);
 }
@@ -199,7 +221,8 @@ __device__ __forceinline__ int32_t id_of(const int32_t* col_id, int32_t j) {
 }
 
 // warp-cooperative insertion of (d, c) into the sorted list of `row`; returns the new k-th best
-__device__ __forceinline__ float list_insert(SmemLayout& sm, int row, float d, int32_t c, int k, int lane, const int32_t* col_id) {
+template <typename SM>
+__device__ __forceinline__ float list_insert(SM& sm, int row, float d, int32_t c, int k, int lane, const int32_t* col_id) {
   float ed = sm.list_d[row][lane];
   int32_t ej = sm.list_j[row][lane];
   bool before = ed < d;
@@ -223,10 +246,10 @@ __device__ __forceinline__ float list_insert(SmemLayout& sm, int row, float d, i
 template <int FLAGS, int WARPS>
 __device__ __noinline__ void process_row_pair(const Params& P, int par, int warp, int lane, int lr0,
                                               int64_t row_base, int64_t col_base) {
-  SmemLayout& sm = smem();
+  auto& sm = smem<WARPS>();
   const ColScalars& cs = sm.cols[par];
   constexpr bool F_TD = (FLAGS & 1) != 0, F_GCCOV = (FLAGS & 2) != 0, F_MASK = (FLAGS & 4) != 0, F_TOPK = (FLAGS & 8) != 0;
-  constexpr int QCAP = QTOTAL / WARPS;
+  constexpr int QCAP = Cfg<WARPS>::QT / WARPS;
   const int ty = lane >> 4, tx = lane & 15;
   const int lr = lr0 + ty;
   const int64_t gi = row_base + lr;
@@ -334,10 +357,10 @@ __device__ __forceinline__ bool cov_predicate(double cu, double cc, double lo, d
 template <int FLAGS, int WARPS>
 __device__ __noinline__ void drain_queue(const Params& P, int par, int warp, int lane, int qn,
                                          int64_t row_base, int64_t col_base) {
-  SmemLayout& sm = smem();
+  auto& sm = smem<WARPS>();
   const ColScalars& cs = sm.cols[par];
   constexpr bool F_TD = (FLAGS & 1) != 0, F_GCCOV = (FLAGS & 2) != 0, F_TOPK = (FLAGS & 8) != 0;
-  constexpr int QCAP = QTOTAL / WARPS, RW = TILE / WARPS;
+  constexpr int QCAP = Cfg<WARPS>::QT / WARPS, RW = Cfg<WARPS>::TROWS / WARPS;
   constexpr uint32_t ALL_BIT = 1u << 31, CAND_BIT = 1u << 30, CODE_MASK = (1u << 11) - 1u;
   const int64_t n = P.n;
   const bool has_gc = F_GCCOV && P.gc != nullptr, has_cov = F_GCCOV && P.cov != nullptr;
@@ -469,8 +492,8 @@ template <int FLAGS, int WARPS>
 __device__ __noinline__ void test_row_pair(int par, int warp, int lane, int i, int flags, int ncol, int k, float d0,
                                            float d1, float d2, float d3, float d4, float d5, float d6, float d7) {
   constexpr bool F_TD = (FLAGS & 1) != 0, F_TOPK = (FLAGS & 8) != 0;
-  constexpr int QCAP = QTOTAL / WARPS, RW = TILE / WARPS;
-  SmemLayout& sm = smem();
+  constexpr int QCAP = Cfg<WARPS>::QT / WARPS, RW = Cfg<WARPS>::TROWS / WARPS;
+  auto& sm = smem<WARPS>();
   const ColScalars& cs = sm.cols[par];
   const int ty = lane >> 4, tx = lane & 15;
   const int lr = warp * RW + 2 * i + ty;
@@ -520,10 +543,11 @@ __device__ __noinline__ void test_row_pair(int par, int warp, int lane, int i, i
 // that buffer was last read by the epilogues of tile ctile-2, and the empty-barrier wait (chunk qg - NSTAGE, which
 // belongs to tile ctile-1 because NSTAGE <= NKC, has been consumed by every warp) implies those are over.
 // (Inlined: an out-of-line call was 1.5 % slower, profiles/r01_pairs_notes.md.)
-template <int FLAGS>
+template <int FLAGS, int WARPS>
 __device__ __forceinline__ void issue_chunk(const CUtensorMap* tmap, const Params& P, uint32_t qg, int ctile, int kc, int par) {
   constexpr bool F_TD = (FLAGS & 1) != 0, F_GCCOV = (FLAGS & 2) != 0;
-  SmemLayout& sm = smem();
+  constexpr int NSTAGE = Cfg<WARPS>::NST;
+  auto& sm = smem<WARPS>();
   const bool has_gc = F_GCCOV && P.gc != nullptr, has_cov = F_GCCOV && P.cov != nullptr;
   const int64_t n = P.n;
   const uint32_t st = qg % NSTAGE;
@@ -584,14 +608,18 @@ __device__ __forceinline__ void issue_chunk(const CUtensorMap* tmap, const Param
 // FLAGS: bit0 TD predicate, bit1 GC and/or coverage predicates, bit2 masks, bit3 top-k, bit4 Euclidean distance
 // (sqrt of the sum of squared differences, FFMA2 instead of the second FADD2) instead of the reference's Manhattan
 template <int FLAGS, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 1) pairs_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Params P) {
+__global__ void __launch_bounds__(WARPS * 32, Cfg<WARPS>::MINB) pairs_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap,
+                                                                           const __grid_constant__ Params P) {
   constexpr bool F_TD = (FLAGS & 1) != 0, F_GCCOV = (FLAGS & 2) != 0, F_MASK = (FLAGS & 4) != 0, F_TOPK = (FLAGS & 8) != 0;
   constexpr bool F_L2 = (FLAGS & 16) != 0;
   auto fin = [](float2 a) -> float { return F_L2 ? __fsqrt_rn(a.x + a.y) : a.x + a.y; };   // accumulator -> distance
-  constexpr int RW = TILE / WARPS;          // rows per warp: 16 or 8
+  constexpr int TROWS = Cfg<WARPS>::TROWS;  // rows of this CTA's row tile: 128, or 64 (one half of a 128-row work item)
+  constexpr int HALVES = TILE / TROWS;      // CTAs that share a work item
+  constexpr int NSTAGE = Cfg<WARPS>::NST, PREFETCH = Cfg<WARPS>::PRE;
+  constexpr int RW = TROWS / WARPS;         // rows per warp: 16 or 8
   constexpr int RI = RW / 2;                // rows per lane: 8 or 4 (lane owns rows warp*RW + 2i + ty)
-  constexpr int QCAP = QTOTAL / WARPS;
-  SmemLayout& sm = smem();
+  constexpr int QCAP = Cfg<WARPS>::QT / WARPS;
+  auto& sm = smem<WARPS>();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t n = P.n;
   const int64_t n_rows = P.row1 - P.row0;
@@ -622,7 +650,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pairs_kernel(const __grid_const
     __syncthreads();                       // everyone is done with the previous item's A tile and lists
     if (tid == 0) sm.item = (int32_t)atomicAdd(P.item_counter, 1u);
     __syncthreads();
-    const int item = sm.item;
+    // a work unit is an item (HALVES = 1) or one 64-row half of it; the halves of an item are consecutive units
+    const int item = sm.item / HALVES;
+    const int lro = (sm.item % HALVES) * TROWS;        // first row of this CTA's part within the 128-row tile
     if (item >= P.n_items) {
       if (P.stats && tid == 0 && blockIdx.x < 1000) {      // DBB_K2_STATS: when did this CTA run out of work
         unsigned long long t;
@@ -654,11 +684,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pairs_kernel(const __grid_const
     // top-k lists); the unused slots of a row tile write empty partial results
     int n_use = P.n_seg;
     if (strided && P.seg_tiles > 0) n_use = max(1, min(P.n_seg, (n_tiles + P.seg_tiles - 1) / P.seg_tiles));
-    const int64_t row_base = P.row0 + (int64_t)rt * TILE;
+    const int64_t row_base = P.row0 + (int64_t)rt * TILE + lro;
+    if (row_base >= P.row1) continue;        // (the second half of a last, short row tile)
     if (strided && seg >= n_use) {
-      for (int lr = tid; lr < TILE; lr += WARPS * 32) {
+      for (int lr = tid; lr < TROWS; lr += WARPS * 32) {
         if (row_base + lr < P.row1) {
-          const int64_t o = ((int64_t)srt * TILE + lr) * P.n_seg + seg;
+          const int64_t o = ((int64_t)srt * TILE + lro + lr) * P.n_seg + seg;
           P.part_cnt[o] = 0;
           P.part_bp[o] = 0;
           if (F_TOPK) for (int e = 0; e < P.k; ++e) { P.part_idx[o * P.k + e] = INT_MAX; P.part_dist[o * P.k + e] = INFINITY; }
@@ -676,11 +707,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pairs_kernel(const __grid_const
 
     // thread 0 doubles as the TMA producer: A tile of this item + its first PREFETCH B chunks
     if (tid == 0) {
-      mbar_arrive_expect_tx(&sm.a_full, NKC * CHUNK_BYTES);
-      for (int kc = 0; kc < NKC; ++kc) tma_load_2d(&sm.a[kc][0][0], &tmap, kc * KCH, (int32_t)row_base, &sm.a_full);
+      mbar_arrive_expect_tx(&sm.a_full, NKC * TROWS * KCH * 4);
+      for (int kc = 0; kc < NKC; ++kc) tma_load_2d(&sm.a[kc][0][0], &tmap_a, kc * KCH, (int32_t)row_base, &sm.a_full);
       for (uint32_t l = 0; l < (uint32_t)PREFETCH && l < item_chunks; ++l) {
         const int ts = t0 + (int)(l / NKC);
-        issue_chunk<FLAGS>(&tmap, P, qbase + l, tile_at(ts), (int)(l % NKC), ts & 1);
+        issue_chunk<FLAGS, WARPS>(&tmap, P, qbase + l, tile_at(ts), (int)(l % NKC), ts & 1);
       }
     }
     // stage row scalars and reset the per-row state of this warp's 16 rows
@@ -698,7 +729,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pairs_kernel(const __grid_const
       sm.rows[lr] = rs;
       sm.cnt[lr] = 0;
       sm.bp_lo[lr] = 0u; sm.bp_hi[lr] = 0u;
-      sm.thr[lr] = F_TOPK ? ((P.gthr && seg >= 0) ? __ldcg(P.gthr + (int64_t)srt * TILE + lr) : INFINITY) : -INFINITY;
+      sm.thr[lr] = F_TOPK ? ((P.gthr && seg >= 0) ? __ldcg(P.gthr + (int64_t)srt * TILE + lro + lr) : INFINITY) : -INFINITY;
     }
     for (int r = 0; r < RW; ++r) {
       sm.list_d[warp * RW + r][lane] = INFINITY;
@@ -733,7 +764,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pairs_kernel(const __grid_const
         if (tid == 0 && l + PREFETCH < item_chunks) {
           const uint32_t ln = l + PREFETCH;
           const int tn = t0 + (int)(ln / NKC);
-          issue_chunk<FLAGS>(&tmap, P, qbase + ln, tile_at(tn), (int)(ln % NKC), tn & 1);
+          issue_chunk<FLAGS, WARPS>(&tmap, P, qbase + ln, tile_at(tn), (int)(ln % NKC), tn & 1);
         }
         mbar_wait(&sm.full[st], (q / NSTAGE) & 1);
         const float* bq = &sm.b[st][tx][0];
@@ -748,7 +779,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pairs_kernel(const __grid_const
         for (int k4 = P.opaque_zero; k4 < KCH / 4; ++k4) {
           const int nkc = (k4 + 1 < KCH / 4) ? kc : (kc + 1 < NKC ? kc + 1 : 0);
           const int nk4 = (k4 + 1 < KCH / 4) ? k4 + 1 : 0;
-          const float* an = a_base + nkc * (TILE * KCH) + nk4 * 4;
+          const float* an = a_base + nkc * (TROWS * KCH) + nk4 * 4;
           #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 bv = *reinterpret_cast<const float4*>(bq + (16 * j) * KCH + k4 * 4);
@@ -832,7 +863,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pairs_kernel(const __grid_const
         if (lane < RW) {
           const int lr = warp * RW + lane;
           const float loc = sm.thr[lr];
-          const unsigned int old = atomicMin(reinterpret_cast<unsigned int*>(P.gthr + (int64_t)srt * TILE + lr), __float_as_uint(loc));
+          const unsigned int old = atomicMin(reinterpret_cast<unsigned int*>(P.gthr + (int64_t)srt * TILE + lro + lr), __float_as_uint(loc));
           sm.thr[lr] = fminf(loc, __uint_as_float(old));
         }
         __syncwarp();
@@ -858,7 +889,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pairs_kernel(const __grid_const
           if (P.count) P.count[gi - P.row0] = sm.cnt[lr];
           if (P.neighbour_bp) P.neighbour_bp[gi - P.row0] = bp;
         } else {
-          const int64_t o = ((int64_t)srt * TILE + lr) * P.n_seg + seg;
+          const int64_t o = ((int64_t)srt * TILE + lro + lr) * P.n_seg + seg;
           P.part_cnt[o] = sm.cnt[lr];
           P.part_bp[o] = bp;
         }
@@ -875,7 +906,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) pairs_kernel(const __grid_const
             if (P.knn_idx) P.knn_idx[(gi - P.row0) * k + lane] = (ej == INT_MAX) ? -1 : id_of(P.col_id, ej);
             if (P.knn_dist) P.knn_dist[(gi - P.row0) * k + lane] = ed;
           } else {
-            const int64_t o = (((int64_t)srt * TILE + lr) * P.n_seg + seg) * k + lane;
+            const int64_t o = (((int64_t)srt * TILE + lro + lr) * P.n_seg + seg) * k + lane;
             P.part_idx[o] = ej;
             P.part_dist[o] = ed;
           }
@@ -951,26 +982,44 @@ int get_encode_fn(EncodeTiledFn* fn) {
   return DBB_OK;
 }
 
-template <int FLAGS>
-int launch_one(unsigned grid, size_t smem, cudaStream_t st, const CUtensorMap& tmap, const Params& P) {
-  // The kernel is templated on the warp count.  16 warps (4x8 register tiles, 128 registers, four warps per
-  // sub-partition) hide the epilogue better (2.1 ms instead of 3.6 ms on C2) but pay 50 % more LDS per FADD2 in the
-  // distance loop (108.8 vs 116.9 G pairs/s without epilogue): the two tie at ~100 G pairs/s, so only the 8-warp
-  // instance is built by default (-DDBB_K2_WARPS16 builds and selects the other; profiles/r01_pairs_notes.md).
+// Warp count of the instance to launch: 4 (two 64-row CTAs per SM, the default) or 8 (one 128-row CTA per SM);
+// DBB_K2_WARPS=8 selects the latter for A/B runs.  -DDBB_K2_WARPS16 builds the 16-warp instance instead of both.
+int pairs_warps() {
 #ifdef DBB_K2_WARPS16
-  DBB_CUDA_TRY(cudaFuncSetAttribute(pairs_kernel<FLAGS, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  pairs_kernel<FLAGS, 16><<<grid, 512, smem, st>>>(tmap, P);
+  return 16;
 #else
-  DBB_CUDA_TRY(cudaFuncSetAttribute(pairs_kernel<FLAGS, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  pairs_kernel<FLAGS, 8><<<grid, 256, smem, st>>>(tmap, P);
+  static const int w = [] { const char* e = getenv("DBB_K2_WARPS"); return (e && atoi(e) == 8) ? 8 : 4; }();
+  return w;
 #endif
+}
+
+template <int FLAGS, int WARPS>
+int launch_inst(int sms, int64_t n_items, cudaStream_t st, const CUtensorMap& tmap_a, const CUtensorMap& tmap, const Params& P) {
+  constexpr size_t smem = sizeof(typename Cfg<WARPS>::Smem);
+  constexpr int per_item = TILE / Cfg<WARPS>::TROWS;
+  DBB_CUDA_TRY(cudaFuncSetAttribute(pairs_kernel<FLAGS, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const unsigned grid = (unsigned)std::min<int64_t>(n_items * per_item, (int64_t)sms * Cfg<WARPS>::MINB);
+  pairs_kernel<FLAGS, WARPS><<<grid, WARPS * 32, smem, st>>>(tmap_a, tmap, P);
   DBB_CUDA_TRY(cudaGetLastError());
   return DBB_OK;
 }
 
-int launch_pairs(int flags, unsigned grid, size_t smem, cudaStream_t st, const CUtensorMap& tmap, const Params& P) {
+template <int FLAGS>
+int launch_one(int sms, int64_t n_items, cudaStream_t st, const CUtensorMap& tmap_a, const CUtensorMap& tmap, const Params& P) {
+  // 16 warps (4x8 register tiles, 128 registers, four warps per sub-partition) hide the epilogue better than 8 (2.1 ms
+  // instead of 3.6 ms on C2's full sweep) but pay 50 % more LDS per FADD2 in the distance loop: a tie
+  // (profiles/r01_pairs_notes.md).
+#ifdef DBB_K2_WARPS16
+  return launch_inst<FLAGS, 16>(sms, n_items, st, tmap_a, tmap, P);
+#else
+  if (pairs_warps() == 8) return launch_inst<FLAGS, 8>(sms, n_items, st, tmap_a, tmap, P);
+  return launch_inst<FLAGS, 4>(sms, n_items, st, tmap_a, tmap, P);
+#endif
+}
+
+int launch_pairs(int flags, int sms, int64_t n_items, cudaStream_t st, const CUtensorMap& tmap_a, const CUtensorMap& tmap, const Params& P) {
   switch (flags) {
-#define DBB_CASE(F) case F: return launch_one<F>(grid, smem, st, tmap, P);
+#define DBB_CASE(F) case F: return launch_one<F>(sms, n_items, st, tmap_a, tmap, P);
     DBB_CASE(0) DBB_CASE(1) DBB_CASE(2) DBB_CASE(3) DBB_CASE(4) DBB_CASE(5) DBB_CASE(6) DBB_CASE(7)
     DBB_CASE(8) DBB_CASE(9) DBB_CASE(10) DBB_CASE(11) DBB_CASE(12) DBB_CASE(13) DBB_CASE(14) DBB_CASE(15)
     DBB_CASE(24) DBB_CASE(25)     // Euclidean: k-NN, optionally with the per-scaffold distance bound and counts
@@ -1056,6 +1105,15 @@ DBB_EXPORT int dbb_pairs_dev(const dbb_pairs_input* in, int64_t row0, int64_t ro
                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) { dbb::set_error("cuTensorMapEncodeTiled failed (%d)", (int)cr); return DBB_ERR_CUDA; }
+  // the row (A) tile of a CTA: the same matrix with a box of the instance's tile rows
+  CUtensorMap tmap_a = tmap;
+  if (pairs_warps() == 4) {
+    cuuint32_t box_a[2] = {(cuuint32_t)KCH, (cuuint32_t)Cfg<4>::TROWS};
+    cr = encode(&tmap_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)in->sig, gdim, gstr, box_a, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) { dbb::set_error("cuTensorMapEncodeTiled failed (%d)", (int)cr); return DBB_ERR_CUDA; }
+  }
 
   Params P;
   P.n = in->n; P.row0 = row0; P.row1 = row1;
@@ -1070,7 +1128,6 @@ DBB_EXPORT int dbb_pairs_dev(const dbb_pairs_input* in, int64_t row0, int64_t ro
   int dev = 0, sms = 0;
   DBB_CUDA_TRY(cudaGetDevice(&dev));
   DBB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const size_t smem = sizeof(SmemLayout);
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t n_rows = row1 - row0;
   const int64_t n_rt = (n_rows + TILE - 1) / TILE;
@@ -1123,10 +1180,10 @@ DBB_EXPORT int dbb_pairs_dev(const dbb_pairs_input* in, int64_t row0, int64_t ro
     DBB_CUDA_TRY(cudaMemsetAsync(P.gthr, 0x7f, (size_t)rem * TILE * 4, st));      // 0x7f7f7f7f = 3.4e38: "no bound yet"
   }
 
-  const unsigned grid = (unsigned)std::min<int64_t>(P.n_items, sms);
+  const unsigned grid = (unsigned)std::min<int64_t>((int64_t)P.n_items * (pairs_warps() == 4 ? 2 : 1), (int64_t)sms * (pairs_warps() == 4 ? 2 : 1));
   int flags = (in->td_bound ? 1 : 0) | ((in->gc || in->cov) ? 2 : 0) | (masks ? 4 : 0) | (out->k > 0 ? 8 : 0);
   if (in->metric == DBB_METRIC_L2) flags |= 16;
-  rc = launch_pairs(flags, grid, smem, st, tmap, P);
+  rc = launch_pairs(flags, sms, P.n_items, st, tmap_a, tmap, P);
   if (rc == DBB_OK && rem > 0 && split_rows > 0) {
     merge_kernel<<<(unsigned)((split_rows + 3) / 4), 128, 0, st>>>(P, split_rows);
     if (cudaGetLastError() != cudaSuccess) { dbb::set_error("merge kernel launch failed"); rc = DBB_ERR_CUDA; }

@@ -78,6 +78,13 @@ int dbb_block_offsets(const int64_t* seq_len, int64_t n_seq, int64_t* blk_off);
 int dbb_pack_ascii_dev(const uint8_t* d_ascii, const int64_t* d_seq_off, const int64_t* d_blk_off,
                        int64_t n_seq, int64_t total_blocks, void* d_codes, void* d_valid, void* stream);
 
+/* The same planes computed on the HOST (AVX2 + BMI2 when the CPU has them, a table loop otherwise; bit-identical to
+ * dbb_pack_ascii_dev): all pointers are host pointers, codes = 16 bytes and valid = 8 bytes per block, scaffold s at
+ * block blk_off[s].  No CUDA call is made.  dbb_tetra_signatures_host uses it on spare host threads for part of every
+ * batch, because packed planes cost 0.375 bytes per base on the host-to-device link against 1 for ASCII. */
+int dbb_pack_ascii_host(const uint8_t* ascii, const int64_t* seq_off, const int64_t* blk_off, int64_t n_seq,
+                        void* codes, void* valid);
+
 /* Same for sequences that are arbitrary slices ascii[begin[s], end[s]) of one buffer (contigs cut out of their
  * scaffolds, preprocess.py:158).  Any of d_codes / d_valid / d_nmask may be NULL.  d_nmask is a third bit plane
  * with the geometry of the validity plane: bit (63 - p) of block word = base p is 'N' or 'n' (splitScaffolds.py:34). */
@@ -118,9 +125,18 @@ int dbb_tetra_count_dev(dbb_count_plan* plan, const void* d_codes, const void* d
                         uint32_t* d_counts, float* d_freq, int64_t freq_stride, void* stream);
 
 /* Whole stage 1 from host memory: ASCII in, counts/freq out (freq is [n_seq][136], dense).
- * Replaces the per-sequence loop of genomicSignatures.py:152-181. */
+ * Replaces the per-sequence loop of genomicSignatures.py:152-181.
+ * The input goes up in batches (DBB_HOST_BATCH_MB, default 256), two in flight.  Pinned (or registered) input is copied
+ * as ASCII.  Pageable input of 8 MB and more per batch is uploaded by two routes at once: the calling thread copies
+ * ASCII from the front of the batch while a few host threads (DBB_HOST_PACK_THREADS; default: the hardware threads /
+ * LOCAL_WORLD_SIZE - 1, at most 16; 0 or DBB_HOST_PACK=0 = off) pack scaffolds from its back with
+ * dbb_pack_ascii_host's code and send 0.375 bytes per base; the split follows the speeds of the two.  Results do not
+ * depend on the route (the planes are bit-identical). */
 int dbb_tetra_signatures_host(const uint8_t* ascii, const int64_t* seq_off, int64_t n_seq,
                               uint32_t* counts, float* freq);
+/* bytes the last dbb_tetra_signatures_host call on the current device sent over the link as ASCII and as host-packed
+ * planes, and the number of packer threads in use (any pointer may be NULL) */
+int dbb_host_upload_stats(int64_t* ascii_bytes, int64_t* plane_bytes, int32_t* pack_threads);
 
 /* ---- stage 2: all-pairs tetranucleotide distance, neighbour predicates and fused top-k ------------
  * tdNeighbours.py:41-51, gcNeighbours.py:43-52, coverageNeighbours.py:41-50 with the bounds of
