@@ -11,8 +11,9 @@
 // GC / coverage arithmetic is FP64 exactly as in the reference; the distance is FP32 (tolerance
 // 2e-6 absolute, tests/).
 //
-// Kernel shape (B200): one persistent CTA per SM, 8 warps (thread 0 also issues the TMA loads).
-//   * CTA tile 128 rows x 128 columns; warp w owns rows 16w..16w+15 against all 128 columns, lane
+// Kernel shape (B200): persistent CTAs (thread 0 also issues the TMA loads), instances by warp count (Cfg<WARPS> below):
+// one 8-warp CTA per SM on 128-row tiles, or -- the default -- two 4-warp CTAs per SM on 64-row halves of them.
+//   * CTA tile 128 (64) rows x 128 columns; warp w owns rows 16w..16w+15 against all 128 columns, lane
 //     (ty = lane/16, tx = lane%16) owns rows 16w+2i+ty and columns tx+16j (i, j < 8): an 8x8 register
 //     tile, accumulated as float2 so the inner loop is two packed FADD2 per two dimensions
 //     (d = a - b ; acc += |d|) -- one FP32 issue slot per pair-dimension instead of two.
