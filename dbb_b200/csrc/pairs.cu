@@ -983,14 +983,18 @@ int get_encode_fn(EncodeTiledFn* fn) {
   return DBB_OK;
 }
 
-// Warp count of the instance to launch: 4 (two 64-row CTAs per SM, the default) or 8 (one 128-row CTA per SM);
-// DBB_K2_WARPS=8 selects the latter for A/B runs.  -DDBB_K2_WARPS16 builds the 16-warp instance instead of both.
-int pairs_warps() {
+// Warp count of the instance to launch: 4 (two 64-row CTAs per SM) or 8 (one 128-row CTA per SM).  The two small CTAs
+// fetch every column tile twice, which is free while the signature matrix sits in L2 and is not once it streams from
+// HBM: measured 4 vs 8 warps C2 (28 MB) 10.49 vs 10.77 ms, C3 (140 MB) 241.6 vs 241.5 ms, C4 (560 MB) 3 456 vs 3 413 ms.
+// So: 4 warps up to 64 MB of signatures, 8 beyond; DBB_K2_WARPS=4|8 forces one for A/B runs.  -DDBB_K2_WARPS16 builds the
+// 16-warp instance instead of both.
+int pairs_warps(int64_t n) {
 #ifdef DBB_K2_WARPS16
   return 16;
 #else
-  static const int w = [] { const char* e = getenv("DBB_K2_WARPS"); return (e && atoi(e) == 8) ? 8 : 4; }();
-  return w;
+  static const int forced = [] { const char* e = getenv("DBB_K2_WARPS"); const int w = (e && *e) ? atoi(e) : 0; return (w == 4 || w == 8) ? w : 0; }();
+  if (forced) return forced;
+  return n * DBB_SIG_STRIDE * 4 <= (64ll << 20) ? 4 : 8;
 #endif
 }
 
@@ -1006,21 +1010,21 @@ int launch_inst(int sms, int64_t n_items, cudaStream_t st, const CUtensorMap& tm
 }
 
 template <int FLAGS>
-int launch_one(int sms, int64_t n_items, cudaStream_t st, const CUtensorMap& tmap_a, const CUtensorMap& tmap, const Params& P) {
+int launch_one(int warps, int sms, int64_t n_items, cudaStream_t st, const CUtensorMap& tmap_a, const CUtensorMap& tmap, const Params& P) {
   // 16 warps (4x8 register tiles, 128 registers, four warps per sub-partition) hide the epilogue better than 8 (2.1 ms
   // instead of 3.6 ms on C2's full sweep) but pay 50 % more LDS per FADD2 in the distance loop: a tie
   // (profiles/r01_pairs_notes.md).
 #ifdef DBB_K2_WARPS16
   return launch_inst<FLAGS, 16>(sms, n_items, st, tmap_a, tmap, P);
 #else
-  if (pairs_warps() == 8) return launch_inst<FLAGS, 8>(sms, n_items, st, tmap_a, tmap, P);
+  if (warps == 8) return launch_inst<FLAGS, 8>(sms, n_items, st, tmap_a, tmap, P);
   return launch_inst<FLAGS, 4>(sms, n_items, st, tmap_a, tmap, P);
 #endif
 }
 
-int launch_pairs(int flags, int sms, int64_t n_items, cudaStream_t st, const CUtensorMap& tmap_a, const CUtensorMap& tmap, const Params& P) {
+int launch_pairs(int flags, int warps, int sms, int64_t n_items, cudaStream_t st, const CUtensorMap& tmap_a, const CUtensorMap& tmap, const Params& P) {
   switch (flags) {
-#define DBB_CASE(F) case F: return launch_one<F>(sms, n_items, st, tmap_a, tmap, P);
+#define DBB_CASE(F) case F: return launch_one<F>(warps, sms, n_items, st, tmap_a, tmap, P);
     DBB_CASE(0) DBB_CASE(1) DBB_CASE(2) DBB_CASE(3) DBB_CASE(4) DBB_CASE(5) DBB_CASE(6) DBB_CASE(7)
     DBB_CASE(8) DBB_CASE(9) DBB_CASE(10) DBB_CASE(11) DBB_CASE(12) DBB_CASE(13) DBB_CASE(14) DBB_CASE(15)
     DBB_CASE(24) DBB_CASE(25)     // Euclidean: k-NN, optionally with the per-scaffold distance bound and counts
@@ -1108,7 +1112,8 @@ DBB_EXPORT int dbb_pairs_dev(const dbb_pairs_input* in, int64_t row0, int64_t ro
   if (cr != CUDA_SUCCESS) { dbb::set_error("cuTensorMapEncodeTiled failed (%d)", (int)cr); return DBB_ERR_CUDA; }
   // the row (A) tile of a CTA: the same matrix with a box of the instance's tile rows
   CUtensorMap tmap_a = tmap;
-  if (pairs_warps() == 4) {
+  const int warps = pairs_warps(in->n);
+  if (warps == 4) {
     cuuint32_t box_a[2] = {(cuuint32_t)KCH, (cuuint32_t)Cfg<4>::TROWS};
     cr = encode(&tmap_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)in->sig, gdim, gstr, box_a, estr,
                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -1181,10 +1186,10 @@ DBB_EXPORT int dbb_pairs_dev(const dbb_pairs_input* in, int64_t row0, int64_t ro
     DBB_CUDA_TRY(cudaMemsetAsync(P.gthr, 0x7f, (size_t)rem * TILE * 4, st));      // 0x7f7f7f7f = 3.4e38: "no bound yet"
   }
 
-  const unsigned grid = (unsigned)std::min<int64_t>((int64_t)P.n_items * (pairs_warps() == 4 ? 2 : 1), (int64_t)sms * (pairs_warps() == 4 ? 2 : 1));
+  const unsigned grid = (unsigned)std::min<int64_t>((int64_t)P.n_items * (warps == 4 ? 2 : 1), (int64_t)sms * (warps == 4 ? 2 : 1));
   int flags = (in->td_bound ? 1 : 0) | ((in->gc || in->cov) ? 2 : 0) | (masks ? 4 : 0) | (out->k > 0 ? 8 : 0);
   if (in->metric == DBB_METRIC_L2) flags |= 16;
-  rc = launch_pairs(flags, sms, P.n_items, st, tmap_a, tmap, P);
+  rc = launch_pairs(flags, warps, sms, P.n_items, st, tmap_a, tmap, P);
   if (rc == DBB_OK && rem > 0 && split_rows > 0) {
     merge_kernel<<<(unsigned)((split_rows + 3) / 4), 128, 0, st>>>(P, split_rows);
     if (cudaGetLastError() != cudaSuccess) { dbb::set_error("merge kernel launch failed"); rc = DBB_ERR_CUDA; }

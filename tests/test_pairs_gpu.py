@@ -445,3 +445,19 @@ def test_c4_law_eight_ranks_against_the_oracle():
                                 part['count'][tp].cpu().numpy(), part['neighbour_bp'][tp].cpu().numpy(), sig32, meta.length, 20, ot)
         assert part['tiles_visited'] < part['tiles_total']
     assert bool((seen == 1).all())
+
+
+def test_eight_warp_instance_passes_the_same_tests():
+    """The pair kernel has two instances (csrc/pairs.cu, Cfg<WARPS>): two 4-warp CTAs per SM on 64-row half tiles while the
+    signature matrix fits L2, one 8-warp CTA per SM on 128-row tiles beyond.  The inputs of this file are small, so the
+    8-warp instance is forced here for the whole file in a child process."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get('DBB_K2_WARPS'):
+        pytest.skip('already a forced-instance run')
+    env = dict(os.environ, DBB_K2_WARPS='8')
+    r = subprocess.run([sys.executable, '-m', 'pytest', os.path.abspath(__file__), '-m', 'gpu', '-q', '-x', '-k', 'not eight_warp'],
+                       env=env, capture_output=True, text=True, timeout=900,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
