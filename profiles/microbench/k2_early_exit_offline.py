@@ -25,7 +25,7 @@ from oracle import c_oracle                                     # noqa: E402  (o
 
 scale = float(sys.argv[1]) if len(sys.argv) > 1 else 0.2
 n_sample = int(sys.argv[2]) if len(sys.argv) > 2 else 1500
-TD_PER = 95
+TD_PER = 80
 T, K, KCH = 128, 20, 28
 
 cache = '/tmp/dbb_c2_sig_%g.npz' % scale
