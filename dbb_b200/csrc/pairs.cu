@@ -751,8 +751,12 @@ __global__ void __launch_bounds__(WARPS * 32, Cfg<WARPS>::MINB) pairs_kernel(con
 #else
 #define DBB_LAP(var)
 #endif
+    float thr_pub = INFINITY;              // what this lane last published for its row (lanes < RW)
     for (int ts = t0; ts < t1; ++ts) {
       const int ct = tile_at(ts);
+      // the bound the other segments of this row tile have proven by now: requested here, used after the K loop
+      float thr_seen = INFINITY;
+      if (F_TOPK && P.gthr && seg >= 0 && lane < RW) thr_seen = __ldcg(P.gthr + (int64_t)srt * TILE + lro + warp * RW + lane);
       float2 acc[RI][8];
       #pragma unroll
       for (int i = 0; i < RI; ++i)
@@ -860,12 +864,16 @@ __global__ void __launch_bounds__(WARPS * 32, Cfg<WARPS>::MINB) pairs_kernel(con
         // exchange with the other segments of this row tile: publish this list's k-th best (once it has one) and pick
         // up the smallest one published so far -- every full list proves an upper bound of the row's final k-th best,
         // so candidates above it cannot be in the merged top-k (ties pass: the tests are <=)
+        // (the load was issued before the K loop and the publication returns nothing, so neither waits for L2)
         __syncwarp();
         if (lane < RW) {
           const int lr = warp * RW + lane;
           const float loc = sm.thr[lr];
-          const unsigned int old = atomicMin(reinterpret_cast<unsigned int*>(P.gthr + (int64_t)srt * TILE + lro + lr), __float_as_uint(loc));
-          sm.thr[lr] = fminf(loc, __uint_as_float(old));
+          if (loc < thr_pub) {
+            atomicMin(reinterpret_cast<unsigned int*>(P.gthr + (int64_t)srt * TILE + lro + lr), __float_as_uint(loc));
+            thr_pub = loc;
+          }
+          sm.thr[lr] = fminf(loc, thr_seen);
         }
         __syncwarp();
       }
