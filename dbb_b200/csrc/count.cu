@@ -470,7 +470,8 @@ int upload_tables() {
 }
 
 // The kernel instantiation of a class: warps per item (= per CTA) and minimum CTAs per SM are the measured best
-// (profiles/r02_k1_classes_by_length.txt); DBB_K1_WPI<S> overrides exist for tuning sweeps.
+// (profiles/r02_k1_classes_by_length.txt; 16 instead of 12 CTAs per SM, i.e. 62 instead of 77 registers: S = 2 class +1.5 %,
+// S = 3 class -2 % on C2); DBB_K1_WPI<S> / DBB_K1_MINB<S> overrides exist for tuning sweeps.
 struct ClassCfg { const void* fn; int threads; size_t smem; int S; };
 template <int S, int WPI, int MINB>
 ClassCfg make_cfg() {
@@ -479,8 +480,8 @@ ClassCfg make_cfg() {
 const ClassCfg& class_cfg(int c) {
   static const ClassCfg cfg[4] = {
       make_cfg<1, 1, 16>(),
-      env_i64("DBB_K1_WPI2", 2) >= 2 ? make_cfg<2, 2, 12>() : make_cfg<2, 1, 16>(),
-      env_i64("DBB_K1_WPI3", 2) >= 4 ? make_cfg<3, 4, 8>() : env_i64("DBB_K1_WPI3", 2) >= 2 ? make_cfg<3, 2, 12>() : make_cfg<3, 1, 16>(),
+      env_i64("DBB_K1_WPI2", 2) >= 2 ? (env_i64("DBB_K1_MINB2", 16) >= 16 ? make_cfg<2, 2, 16>() : make_cfg<2, 2, 12>()) : make_cfg<2, 1, 16>(),
+      env_i64("DBB_K1_WPI3", 2) >= 4 ? make_cfg<3, 4, 8>() : env_i64("DBB_K1_WPI3", 2) >= 2 ? (env_i64("DBB_K1_MINB3", 12) >= 16 ? make_cfg<3, 2, 16>() : make_cfg<3, 2, 12>()) : make_cfg<3, 1, 16>(),
       env_i64("DBB_K1_WPI4", 8) >= 8 ? make_cfg<4, 8, 6>() : env_i64("DBB_K1_WPI4", 8) >= 4 ? make_cfg<4, 4, 6>() : make_cfg<4, 2, 6>()};
   return cfg[c];
 }
