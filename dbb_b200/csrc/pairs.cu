@@ -992,10 +992,10 @@ int get_encode_fn(EncodeTiledFn* fn) {
 }
 
 // Warp count of the instance to launch: 4 (two 64-row CTAs per SM) or 8 (one 128-row CTA per SM).  The two small CTAs
-// fetch every column tile twice, which is free while the signature matrix sits in L2 and is not once it streams from
-// HBM: measured 4 vs 8 warps C2 (28 MB) 10.49 vs 10.77 ms, C3 (140 MB) 241.6 vs 241.5 ms, C4 (560 MB) 3 456 vs 3 413 ms.
-// So: 4 warps up to 64 MB of signatures, 8 beyond; DBB_K2_WARPS=4|8 forces one for A/B runs.  -DDBB_K2_WARPS16 builds the
-// 16-warp instance instead of both.
+// fetch every column tile twice, which is free while the signature matrix sits in L2.  Measured 4 vs 8 warps: C2 (28 MB of
+// signatures) 10.49 vs 10.77 ms; C3 (140 MB) 241.6 vs 241.5 ms; C4 (560 MB) 3 456 vs 3 460 ms -- a gain where the matrix
+// is L2-resident and the items are short, none beyond.  So: 4 warps up to 64 MB of signatures, 8 (the instance with half
+// the L2 traffic) beyond; DBB_K2_WARPS=4|8 forces one for A/B runs.  -DDBB_K2_WARPS16 builds the 16-warp instance instead.
 int pairs_warps(int64_t n) {
 #ifdef DBB_K2_WARPS16
   return 16;
