@@ -224,6 +224,58 @@ __device__ __forceinline__ void fold_histogram(uint32_t sb, int lane, int warp) 
   }
 }
 
+// Fold of the 7-mer histogram (S = 4) in TWO read passes instead of four (the generic fold above reads the whole
+// histogram once per window offset: 4 x 32 KB = 1 024 wavefronts, 35 % of the shared-memory pipe of a 96 kb scaffold):
+//   pass "suffix": thread <-> t = (b3 b4 b5 b6), the low 8 bits of the word index; the 32 words (b0_lo b1 b2 | t) are 32
+//     conflict-free 32-bit loads.  Offset 3 (code t) is the sum of all of them, offset 2 (code b2 b3 b4 b5) sums over
+//     b0, b1 in the thread and over b6 across the four neighbouring lanes;
+//   pass "prefix": thread <-> rho = (b0_lo b1 b2 b3 b4), a run of 16 consecutive words (b5 b6) read as four rotated
+//     128-bit loads.  Offset 1 (code b1 b2 b3 b4) adds both halves (b0_hi), b0_lo arrives from the other rho through the
+//     atomic; offset 0 (codes c and c | 128 in the low / high halves) sums over b4 across the four neighbouring lanes.
+// Every bin is read exactly twice: 512 wavefronts + ~100 for shuffles and the updates of c4.  Read-only (the caller
+// re-zeroes the histogram behind a barrier, as for the other S).
+template <int WPI>
+__device__ __forceinline__ void fold_histogram4(uint32_t sb, int tid, int lane) {
+  constexpr int NT = 32 * WPI;
+  static_assert(256 % NT == 0, "whole warps must run every iteration of the loops below (they shuffle)");
+  const uint32_t hs = sb + 4 * OFF_HS;
+  #pragma unroll 1
+  for (int t = tid; t < 256; t += NT) {
+    uint32_t m3 = 0, m2[4] = {0u, 0u, 0u, 0u};
+    #pragma unroll
+    for (int it = 0; it < 32; ++it) {               // it = (b0_lo b1 b2)
+      const uint32_t sv = halves(lds(hs + 4 * ((it << 8) | t)));
+      m3 += sv;
+      m2[it & 3] += sv;
+    }
+    red_add(sb + 4 * (OFF_C4 + t), m3);
+    #pragma unroll
+    for (int j = 0; j < 4; ++j) {                   // sum over b6 = the two low lane bits (t = tid + i NT: lane bits = t bits)
+      m2[j] += __shfl_xor_sync(0xffffffffu, m2[j], 1);
+      m2[j] += __shfl_xor_sync(0xffffffffu, m2[j], 2);
+    }
+    const int j = t & 3;                            // lane j of the four publishes b2 = j
+    const uint32_t v = j == 0 ? m2[0] : j == 1 ? m2[1] : j == 2 ? m2[2] : m2[3];
+    red_add(sb + 4 * (OFF_C4 + ((j << 6) | (t >> 2))), v);
+  }
+  #pragma unroll 1
+  for (int rho = tid; rho < 512; rho += NT) {
+    uint32_t a = 0;                                 // packed halves: b0_hi = 0 / 1 (no half can wrap: an item is <= 65 535 super-k-mers)
+    #pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int ch = (r + (lane >> 1)) & 3;         // the eight lanes of a 128-bit wavefront hit eight bank groups
+      a += sum4(lds128(hs + 4 * (rho * 16 + 4 * ch)));
+    }
+    red_add(sb + 4 * (OFF_C4 + (rho & 255)), halves(a));
+    a += __shfl_xor_sync(0xffffffffu, a, 1);        // sum over b4 = the two low lane bits
+    a += __shfl_xor_sync(0xffffffffu, a, 2);
+    if ((rho & 3) == 0) {
+      red_add(sb + 4 * (OFF_C4 + (rho >> 2)), a & 0xffffu);
+      red_add(sb + 4 * (OFF_C4 + (rho >> 2) + 128), a >> 16);
+    }
+  }
+}
+
 template <int WPI>
 __device__ __forceinline__ void group_sync() {
   if (WPI == 1) __syncwarp(); else __syncthreads();
@@ -327,7 +379,8 @@ __global__ void __launch_bounds__(32 * WPI, MINB) count_kernel(const Item* __res
     if (c_debug_skip_flush) { it = it_n; item = item_n; if (!has_n) break; continue; }
 
     if (S > 1) {
-      fold_histogram<S, WPI>(sb, lane, warp);
+      if (S == 4) fold_histogram4<WPI>(sb, (int)tid, lane);
+      else fold_histogram<S, WPI>(sb, lane, warp);
       group_sync<WPI>();                                    // every marginal is in c4, nobody reads the histogram any more
       for (int x = tid * 4; x < WORDS; x += 128 * WPI) sts128_zero(sb + 4 * (OFF_HS + x));
     }
