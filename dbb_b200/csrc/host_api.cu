@@ -487,8 +487,14 @@ DBB_EXPORT int dbb_tetra_signatures_host(const uint8_t* ascii, const int64_t* se
   if (!ctx->sig) ctx->sig = new dbb::SigState();
   Lane* lanes = ctx->sig->lanes;
   ctx->sig->ascii_bytes = ctx->sig->plane_bytes = 0;
+  // batch size: pinned input streams best in small batches (the last batch's count + copy-back is the only part the
+  // link does not overlap: C2 53.5 / 52.5 / 51.6 / 48.9 Gbp/s for 32 / 128 / 256 / 512 MB), pageable input in large ones
+  // (every batch ends with the packer threads meeting: 23.6 / 37.9 / 44.4 / 47.7 Gbp/s)
   const char* env = getenv("DBB_HOST_BATCH_MB");
-  const int64_t batch_bytes = (env && *env ? atoll(env) : 256) << 20;
+  cudaPointerAttributes pattr;
+  const bool in_pageable = ascii && (cudaPointerGetAttributes(&pattr, ascii) != cudaSuccess || pattr.type == cudaMemoryTypeUnregistered);
+  cudaGetLastError();
+  const int64_t batch_bytes = (env && *env ? atoll(env) : (in_pageable && pack_threads() > 0) ? 512 : 32) << 20;
   for (int i = 0; i < 2; ++i) {
     Lane& L = lanes[i];
     if (L.st) continue;

@@ -126,8 +126,8 @@ int dbb_tetra_count_dev(dbb_count_plan* plan, const void* d_codes, const void* d
 
 /* Whole stage 1 from host memory: ASCII in, counts/freq out (freq is [n_seq][136], dense).
  * Replaces the per-sequence loop of genomicSignatures.py:152-181.
- * The input goes up in batches (DBB_HOST_BATCH_MB, default 256), two in flight.  Pinned (or registered) input is copied
- * as ASCII.  Pageable input of 8 MB and more per batch is uploaded by two routes at once: the calling thread copies
+ * The input goes up in batches (DBB_HOST_BATCH_MB; default 32 MB for pinned, 512 MB for pageable input), two in flight.
+ * Pinned (or registered) input is copied as ASCII.  Pageable input of 8 MB and more per batch is uploaded by two routes at once: the calling thread copies
  * ASCII from the front of the batch while a few host threads (DBB_HOST_PACK_THREADS; default: the hardware threads /
  * LOCAL_WORLD_SIZE - 1, at most 16; 0 or DBB_HOST_PACK=0 = off) pack scaffolds from its back with
  * dbb_pack_ascii_host's code and send 0.375 bytes per base; the split follows the speeds of the two.  Results do not
