@@ -112,6 +112,7 @@ SIGNATURES = {
     'dbb_count_class_limits': (ctypes.c_int, [c_vp]),
     'dbb_tetra_count_dev': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
     'dbb_tetra_signatures_host': (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
+    'dbb_tetra_signatures_host_ptrs': (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
     'dbb_host_upload_stats': (ctypes.c_int, [c_vp, c_vp, c_vp]),
     'dbb_pairs_dev': (ctypes.c_int, [ctypes.POINTER(PairsInput), c_i64, c_i64, ctypes.POINTER(PairsOutput), c_vp]),
     'dbb_pairs_scratch_bytes': (c_i64, [c_i64, c_i64, c_i32]),

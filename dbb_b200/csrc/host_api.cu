@@ -319,20 +319,25 @@ constexpr int64_t HYBRID_MIN_BYTES = 8 << 20;  // smaller batches go up as ASCII
 // packers carry 33 / 48 / 60 % of the bases) while the sum of the two routes stays at ~50 GB/s of input read from host
 // memory, i.e. 49-50 Gbp/s against 51.7 for the plain copy -- the pinned line is bound by reading the input once, not
 // by the bytes on the link.  DBB_HOST_PACK=0: ASCII only; =all: packers only; =hybrid: mixed upload for pinned input too.
-int hybrid_upload(Lane& L, SigState& S, int device, const uint8_t* base, int64_t ns, int64_t nbytes, int64_t* n_ascii) {
+int hybrid_upload(Lane& L, SigState& S, int device, const uint8_t* base, const uint8_t* const* ptrs, int64_t ns, int64_t nbytes,
+                  int64_t* n_ascii) {
   *n_ascii = ns;
   const int n_thr = pack_threads();
   static const int mode = [] {
     const char* m = getenv("DBB_HOST_PACK");
     return !m ? 0 : strcmp(m, "all") == 0 ? 2 : strcmp(m, "hybrid") == 0 ? 1 : 0;
   }();
-  const bool pack_all = mode == 2;
-  cudaPointerAttributes attr;
-  const bool pageable = cudaPointerGetAttributes(&attr, base) != cudaSuccess || attr.type == cudaMemoryTypeUnregistered;
-  cudaGetLastError();                                        // (an unknown host pointer is reported as an error on old drivers)
-  if (n_thr <= 0 || (!pack_all && nbytes < HYBRID_MIN_BYTES) || (!pageable && mode == 0))
-    return h2d_any(L, device, L.ascii.p, base, (size_t)nbytes);
-  if (!S.pool || S.pool_threads != n_thr) { delete S.pool; S.pool = new HostPool(n_thr); S.pool_threads = n_thr; }
+  // scattered sequences (ptrs: one host pointer per scaffold, dbb_tetra_signatures_host_ptrs) have no ASCII route: a copy
+  // per scaffold would be thousands of small transfers; they all go through the packers
+  const bool pack_all = mode == 2 || ptrs != nullptr;
+  if (!ptrs) {
+    cudaPointerAttributes attr;
+    const bool pageable = cudaPointerGetAttributes(&attr, base) != cudaSuccess || attr.type == cudaMemoryTypeUnregistered;
+    cudaGetLastError();                                        // (an unknown host pointer is reported as an error on old drivers)
+    if (n_thr <= 0 || (!pack_all && nbytes < HYBRID_MIN_BYTES) || (!pageable && mode == 0))
+      return h2d_any(L, device, L.ascii.p, base, (size_t)nbytes);
+  }
+  if (n_thr > 0 && (!S.pool || S.pool_threads != n_thr)) { delete S.pool; S.pool = new HostPool(n_thr); S.pool_threads = n_thr; }
   if (!L.st2) {
     DBB_CUDA_TRY(cudaStreamCreateWithFlags(&L.st2, cudaStreamNonBlocking));
     DBB_CUDA_TRY(cudaEventCreateWithFlags(&L.ev2, cudaEventDisableTiming));
@@ -341,6 +346,20 @@ int hybrid_upload(Lane& L, SigState& S, int device, const uint8_t* base, int64_t
   const int64_t nblk = L.h_blk[ns];
   DBB_TRY(L.pk_codes.reserve((size_t)std::max<int64_t>(nblk, 1) * 16));
   DBB_TRY(L.pk_valid.reserve((size_t)std::max<int64_t>(nblk, 1) * 8));
+  if (ptrs && (n_thr <= 0 || nbytes < (1 << 20))) {
+    // no packer threads (or a batch too small to be worth waking them): the calling thread packs
+    for (int64_t s = 0; s < ns; ++s)
+      dbb::host_pack_sequence(ptrs[s], L.h_off[s + 1] - L.h_off[s], reinterpret_cast<uint32_t*>(L.pk_codes.p + 16 * L.h_blk[s]),
+                              reinterpret_cast<uint64_t*>(L.pk_valid.p + 8 * L.h_blk[s]));
+    if (nblk > 0) {
+      DBB_CUDA_TRY(cudaMemcpyAsync(L.codes.p, L.pk_codes.p, (size_t)nblk * 16, cudaMemcpyHostToDevice, L.st));
+      DBB_CUDA_TRY(cudaMemcpyAsync(L.valid.p, L.pk_valid.p, (size_t)nblk * 8, cudaMemcpyHostToDevice, L.st));
+    }
+    *n_ascii = 0;
+    S.ascii_bytes -= nbytes;
+    S.plane_bytes += nblk * 24;
+    return DBB_OK;
+  }
   // units
   L.unit.clear();
   L.unit.push_back(0);
@@ -359,12 +378,12 @@ int hybrid_upload(Lane& L, SigState& S, int device, const uint8_t* base, int64_t
   std::atomic<uint8_t>* done = L.unit_done.get();
   uint8_t* pkc = L.pk_codes.p;
   uint8_t* pkv = L.pk_valid.p;
-  S.pool->start([&, h_off, h_blk, unit, done, pkc, pkv, base](int) {
+  S.pool->start([&, h_off, h_blk, unit, done, pkc, pkv, base, ptrs](int) {
     for (;;) {
       int64_t u;
       { std::lock_guard<std::mutex> lk(mu); if (front > back) return; u = back--; }
       for (int64_t s = unit[u]; s < unit[u + 1]; ++s)
-        dbb::host_pack_sequence(base + h_off[s], h_off[s + 1] - h_off[s], reinterpret_cast<uint32_t*>(pkc + 16 * h_blk[s]),
+        dbb::host_pack_sequence(ptrs ? ptrs[s] : base + h_off[s], h_off[s + 1] - h_off[s], reinterpret_cast<uint32_t*>(pkc + 16 * h_blk[s]),
                                 reinterpret_cast<uint64_t*>(pkv + 8 * h_blk[s]));
       done[u].store(1, std::memory_order_release);
     }
@@ -421,23 +440,32 @@ int hybrid_upload(Lane& L, SigState& S, int device, const uint8_t* base, int64_t
   return DBB_OK;
 }
 
-int submit_batch(Lane& L, SigState& S, int device, const uint8_t* ascii, const int64_t* seq_off, int64_t s0, int64_t s1,
-                 bool want_counts, bool want_freq) {
+// where the sequences of a call live: back to back in one buffer (ascii + seq_off) or one host pointer per scaffold
+struct SeqSource {
+  const uint8_t* ascii = nullptr;
+  const int64_t* seq_off = nullptr;
+  const uint8_t* const* ptrs = nullptr;
+  const int64_t* lens = nullptr;
+  int64_t len(int64_t s) const { return ptrs ? lens[s] : seq_off[s + 1] - seq_off[s]; }
+};
+
+int submit_batch(Lane& L, SigState& S, int device, const SeqSource& src, int64_t s0, int64_t s1, bool want_counts, bool want_freq) {
   const int64_t ns = s1 - s0;
-  const int64_t byte0 = seq_off[s0], nbytes = seq_off[s1] - byte0;
   L.s0 = s0; L.s1 = s1;
   L.h_off.resize(ns + 1);
   L.h_blk.resize(ns + 1);
-  int64_t acc = 0;
+  int64_t acc = 0, bytes = 0;
   for (int64_t i = 0; i < ns; ++i) {
-    L.h_off[i] = seq_off[s0 + i] - byte0;
+    const int64_t len = src.len(s0 + i);
+    L.h_off[i] = bytes;
     L.h_blk[i] = acc;
-    acc += dbb_packed_blocks(seq_off[s0 + i + 1] - seq_off[s0 + i]);
+    bytes += len;
+    acc += dbb_packed_blocks(len);
   }
-  L.h_off[ns] = nbytes;
+  L.h_off[ns] = bytes;
   L.h_blk[ns] = acc;
-  const int64_t nblk = acc;
-  DBB_TRY(L.ascii.reserve((size_t)std::max<int64_t>(nbytes, 16)));
+  const int64_t nblk = acc, nbytes = bytes;
+  if (!src.ptrs) DBB_TRY(L.ascii.reserve((size_t)std::max<int64_t>(nbytes, 16)));
   DBB_TRY(L.seq_off.reserve((ns + 1) * 8));
   DBB_TRY(L.blk_off.reserve((ns + 1) * 8));
   DBB_TRY(L.codes.reserve((size_t)std::max<int64_t>(nblk, 1) * 16 + 16));
@@ -450,7 +478,7 @@ int submit_batch(Lane& L, SigState& S, int device, const uint8_t* ascii, const i
   DBB_CUDA_TRY(cudaMemcpyAsync(L.blk_off.p, L.h_blk.data(), (ns + 1) * 8, cudaMemcpyHostToDevice, L.st));
   int64_t n_ascii = ns;                 // scaffolds [0, n_ascii) arrive as ASCII, the others as host-packed planes
   S.ascii_bytes += nbytes;
-  DBB_TRY(hybrid_upload(L, S, device, ascii + byte0, ns, nbytes, &n_ascii));
+  DBB_TRY(hybrid_upload(L, S, device, src.ptrs ? nullptr : src.ascii + src.seq_off[s0], src.ptrs ? src.ptrs + s0 : nullptr, ns, nbytes, &n_ascii));
   if (n_ascii > 0)
     DBB_TRY(dbb_pack_ascii_dev((const uint8_t*)L.ascii.p, (const int64_t*)L.seq_off.p, (const int64_t*)L.blk_off.p, n_ascii,
                                L.h_blk[n_ascii], L.codes.p, L.valid.p, L.st));
@@ -469,17 +497,12 @@ int collect_batch(Lane& L, uint32_t* counts, float* freq) {
 
 }  // namespace
 
-DBB_EXPORT int dbb_tetra_signatures_host(const uint8_t* ascii, const int64_t* seq_off, int64_t n_seq,
-                                         uint32_t* counts, float* freq) {
-  DBB_REQUIRE(n_seq >= 0, "negative n_seq");
-  if (n_seq == 0) return DBB_OK;
-  DBB_REQUIRE(seq_off != nullptr && (counts || freq), "NULL argument");
-  DBB_REQUIRE(ascii != nullptr || seq_off[n_seq] == seq_off[0], "ascii is NULL");
-  for (int64_t s = 0; s < n_seq; ++s) DBB_REQUIRE(seq_off[s + 1] >= seq_off[s], "seq_off must be non-decreasing");
+namespace {
 
-  // batches of ~batch_bytes of sequence, two in flight (copy of batch b+1 overlaps compute of batch b).  The
-  // lanes (streams, device buffers, count plans) belong to the default context of the current device and only grow:
-  // a per-sequence caller such as GenomicSignatures.seqSignature pays no allocation after its first call.
+// batches of ~batch_bytes of sequence, two in flight (upload of batch b+1 overlaps compute of batch b).  The lanes
+// (streams, device buffers, count plans) belong to the default context of the current device and only grow: a
+// per-sequence caller such as GenomicSignatures.seqSignature pays no allocation after its first call.
+int signatures_host_impl(const SeqSource& src, int64_t n_seq, uint32_t* counts, float* freq) {
   dbb_ctx* ctx = nullptr;
   int rc = dbb::ctx_resolve(nullptr, &ctx);
   if (rc != DBB_OK) return rc;
@@ -491,10 +514,13 @@ DBB_EXPORT int dbb_tetra_signatures_host(const uint8_t* ascii, const int64_t* se
   // link does not overlap: C2 53.5 / 52.5 / 51.6 / 48.9 Gbp/s for 32 / 128 / 256 / 512 MB), pageable input in large ones
   // (every batch ends with the packer threads meeting: 23.6 / 37.9 / 44.4 / 47.7 Gbp/s)
   const char* env = getenv("DBB_HOST_BATCH_MB");
-  cudaPointerAttributes pattr;
-  const bool in_pageable = ascii && (cudaPointerGetAttributes(&pattr, ascii) != cudaSuccess || pattr.type == cudaMemoryTypeUnregistered);
-  cudaGetLastError();
-  const int64_t batch_bytes = (env && *env ? atoll(env) : (in_pageable && pack_threads() > 0) ? 512 : 32) << 20;
+  bool big_batches = src.ptrs != nullptr;
+  if (!src.ptrs && src.ascii) {
+    cudaPointerAttributes pattr;
+    big_batches = cudaPointerGetAttributes(&pattr, src.ascii) != cudaSuccess || pattr.type == cudaMemoryTypeUnregistered;
+    cudaGetLastError();
+  }
+  const int64_t batch_bytes = (env && *env ? atoll(env) : (big_batches && pack_threads() > 0) ? 512 : 32) << 20;
   for (int i = 0; i < 2; ++i) {
     Lane& L = lanes[i];
     if (L.st) continue;
@@ -505,12 +531,11 @@ DBB_EXPORT int dbb_tetra_signatures_host(const uint8_t* ascii, const int64_t* se
   int cur = 0;
   bool pending[2] = {false, false};
   while (rc == DBB_OK && s < n_seq) {
-    int64_t e = s;
-    const int64_t b0 = seq_off[s];
-    while (e < n_seq && (e == s || seq_off[e + 1] - b0 <= batch_bytes)) ++e;
+    int64_t e = s, bytes = 0;
+    while (e < n_seq && (e == s || bytes + src.len(e) <= batch_bytes)) { bytes += src.len(e); ++e; }
     Lane& L = lanes[cur];
     if (pending[cur]) { rc = collect_batch(L, counts, freq); pending[cur] = false; if (rc != DBB_OK) break; }
-    rc = submit_batch(L, *ctx->sig, ctx->device, ascii, seq_off, s, e, counts != nullptr, freq != nullptr);
+    rc = submit_batch(L, *ctx->sig, ctx->device, src, s, e, counts != nullptr, freq != nullptr);
     if (rc != DBB_OK) break;
     pending[cur] = true;
     cur ^= 1;
@@ -524,6 +549,34 @@ DBB_EXPORT int dbb_tetra_signatures_host(const uint8_t* ascii, const int64_t* se
     }
   }
   return rc;
+}
+
+}  // namespace
+
+DBB_EXPORT int dbb_tetra_signatures_host(const uint8_t* ascii, const int64_t* seq_off, int64_t n_seq,
+                                         uint32_t* counts, float* freq) {
+  DBB_REQUIRE(n_seq >= 0, "negative n_seq");
+  if (n_seq == 0) return DBB_OK;
+  DBB_REQUIRE(seq_off != nullptr && (counts || freq), "NULL argument");
+  DBB_REQUIRE(ascii != nullptr || seq_off[n_seq] == seq_off[0], "ascii is NULL");
+  for (int64_t s = 0; s < n_seq; ++s) DBB_REQUIRE(seq_off[s + 1] >= seq_off[s], "seq_off must be non-decreasing");
+  SeqSource src;
+  src.ascii = ascii; src.seq_off = seq_off;
+  return signatures_host_impl(src, n_seq, counts, freq);
+}
+
+DBB_EXPORT int dbb_tetra_signatures_host_ptrs(const uint8_t* const* seqs, const int64_t* seq_len, int64_t n_seq,
+                                              uint32_t* counts, float* freq) {
+  DBB_REQUIRE(n_seq >= 0, "negative n_seq");
+  if (n_seq == 0) return DBB_OK;
+  DBB_REQUIRE(seqs != nullptr && seq_len != nullptr && (counts || freq), "NULL argument");
+  for (int64_t s = 0; s < n_seq; ++s) {
+    DBB_REQUIRE(seq_len[s] >= 0, "negative sequence length");
+    DBB_REQUIRE(seq_len[s] == 0 || seqs[s] != nullptr, "NULL sequence pointer");
+  }
+  SeqSource src;
+  src.ptrs = seqs; src.lens = seq_len;
+  return signatures_host_impl(src, n_seq, counts, freq);
 }
 
 DBB_EXPORT int dbb_host_upload_stats(int64_t* ascii_bytes, int64_t* plane_bytes, int32_t* pack_threads_out) {

@@ -89,16 +89,30 @@ class GenomicSignatures(object):
             flat = np.ascontiguousarray(flat, dtype=np.uint8)
             off = np.ascontiguousarray(off, dtype=np.int64)
         else:
-            parts = []
-            for s in seqs:
+            # a list of separate buffers (how the reference holds its sequences): one pointer + length per sequence, no
+            # concatenation -- the library's packer threads read every sequence where it lies
+            n = len(seqs)
+            keep = []
+            ptrs = np.zeros(max(n, 1), dtype=np.uint64)
+            lens = np.zeros(max(n, 1), dtype=np.int64)
+            for i, s in enumerate(seqs):
                 if isinstance(s, str):
                     s = s.encode('latin-1', 'replace')       # non-latin-1 text cannot be ACGT anyway
-                parts.append(np.frombuffer(s, dtype=np.uint8) if not isinstance(s, np.ndarray) else s.astype(np.uint8, copy=False))
-            off = np.zeros(len(parts) + 1, dtype=np.int64)
-            if parts:
-                off[1:] = np.cumsum([p.shape[0] for p in parts])
-            flat = np.concatenate(parts) if parts else np.zeros(0, dtype=np.uint8)
-            flat = np.ascontiguousarray(flat)
+                if not isinstance(s, np.ndarray):
+                    a = np.frombuffer(s, dtype=np.uint8)
+                elif s.dtype == np.uint8 and s.ndim == 1 and s.flags.c_contiguous:
+                    a = s
+                else:
+                    a = np.ascontiguousarray(s, dtype=np.uint8).reshape(-1)
+                keep.append(a)
+                ptrs[i] = a.__array_interface__['data'][0]
+                lens[i] = a.shape[0]
+            counts = np.zeros((n, _lib.NUM_KMERS), dtype=np.uint32) if want_counts else None
+            freq = np.zeros((n, _lib.NUM_KMERS), dtype=np.float32) if want_freq else None
+            if n:
+                _lib.check(_lib.lib().dbb_tetra_signatures_host_ptrs(_lib.ptr(ptrs), _lib.ptr(lens), n, _lib.ptr(counts), _lib.ptr(freq)))
+            del keep
+            return counts, freq
         n = off.shape[0] - 1
         counts = np.zeros((n, _lib.NUM_KMERS), dtype=np.uint32) if want_counts else None
         freq = np.zeros((n, _lib.NUM_KMERS), dtype=np.float32) if want_freq else None

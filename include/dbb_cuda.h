@@ -134,6 +134,11 @@ int dbb_tetra_count_dev(dbb_count_plan* plan, const void* d_codes, const void* d
  * depend on the route (the planes are bit-identical). */
 int dbb_tetra_signatures_host(const uint8_t* ascii, const int64_t* seq_off, int64_t n_seq,
                               uint32_t* counts, float* freq);
+/* The same for sequences that are NOT back to back: one host pointer and one length per scaffold (the reference keeps its
+ * sequences as separate Python strings, seqUtils.readFasta -> genomicSignatures.py:152-181).  Nothing is concatenated:
+ * the packer threads read every scaffold where it lies and only packed planes cross the link. */
+int dbb_tetra_signatures_host_ptrs(const uint8_t* const* seqs, const int64_t* seq_len, int64_t n_seq,
+                                   uint32_t* counts, float* freq);
 /* bytes the last dbb_tetra_signatures_host call on the current device sent over the link as ASCII and as host-packed
  * planes, and the number of packer threads in use (any pointer may be NULL) */
 int dbb_host_upload_stats(int64_t* ascii_bytes, int64_t* plane_bytes, int32_t* pack_threads);

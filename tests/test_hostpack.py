@@ -90,3 +90,30 @@ def test_signatures_host_is_the_same_by_either_upload_route():
     assert int(ascii_only[2]) == 0 and int(ascii_only[1]) > 0          # nothing went up as planes
     assert int(packed_only[1]) == 0 and int(packed_only[2]) > 0        # nothing went up as ASCII
     assert int(mixed[1]) + int(mixed[2]) > 0
+
+
+@pytest.mark.gpu
+def test_class_call_on_a_list_of_separate_buffers_needs_no_concatenation():
+    """GenomicSignatures.signatures(list) -> dbb_tetra_signatures_host_ptrs: str, bytes, uint8 arrays, empty and one-base
+    sequences, each at its own address; same counts as the back-to-back entry point and as the oracle."""
+    from dbb_b200.genomicSignatures import GenomicSignatures
+    from oracle import dbb_oracle as O
+    rng = np.random.RandomState(21)
+    lens = [0, 1, 3, 4, 63, 64, 65, 700, 5000, 130000] + rng.randint(0, 40000, 60).tolist()
+    arrs = [util.random_dna(rng, int(l), 0.02 if i % 4 == 0 else 0.0) for i, l in enumerate(lens)]
+    mixed = [a if i % 3 == 0 else (a.tobytes() if i % 3 == 1 else a.tobytes().decode('latin-1')) for i, a in enumerate(arrs)]
+    gs = GenomicSignatures(4, 1)
+    counts, freq = gs.signatures(mixed)
+    off = np.zeros(len(arrs) + 1, dtype=np.int64)
+    off[1:] = np.cumsum(lens)
+    c2, f2 = gs.signatures((np.concatenate(arrs), off))
+    assert np.array_equal(counts, c2)
+    assert np.array_equal(freq, f2, equal_nan=True)
+    for i in (0, 1, 3, 4, 7, 9, 20):
+        assert np.array_equal(counts[i].astype(np.int64), O.seq_counts_np(arrs[i]))
+    # a batch large enough for the packer threads (several MB) through the same call
+    big = [util.random_dna(rng, 50000) for _ in range(120)]
+    cb, _ = gs.signatures(big, want_freq=False)
+    offb = np.arange(121, dtype=np.int64) * 50000
+    cb2, _ = gs.signatures((np.concatenate(big), offb), want_freq=False)
+    assert np.array_equal(cb, cb2)
