@@ -948,11 +948,17 @@ __global__ void __launch_bounds__(128) merge_kernel(const Params P, int64_t n_sp
     float ed = INFINITY;
     int32_t ej = INT_MAX;
     for (int sgi = 0; sgi < P.n_seg; ++sgi) {
+      // the whole partial list in one coalesced load (lane e holds entry e), then walked through shuffles: no memory
+      // latency inside the insertion loop
+      const int64_t o = (r * P.n_seg + sgi) * k;
+      const float sd = lane < k ? P.part_dist[o + lane] : INFINITY;
+      const int32_t sj = lane < k ? P.part_idx[o + lane] : INT_MAX;
       for (int e = 0; e < k; ++e) {
-        const int64_t o = (r * P.n_seg + sgi) * k + e;
-        const float d = P.part_dist[o];
-        const int32_t c = P.part_idx[o];
+        const float d = __shfl_sync(0xffffffffu, sd, e);
+        const int32_t c = __shfl_sync(0xffffffffu, sj, e);
         if (c == INT_MAX) break;              // lists are sorted: the rest is padding
+        // ... and so is everything behind an entry that is farther than the current k-th best (ties still compare ids)
+        if (d > __shfl_sync(0xffffffffu, ed, k - 1)) break;
         bool before = ed < d;
         if (ed == d) before = id_of(P.col_id, ej) < id_of(P.col_id, c);
         const int pos = __popc(__ballot_sync(0xffffffffu, before));
